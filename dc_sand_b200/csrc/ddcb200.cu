@@ -1,0 +1,559 @@
+// C-ABI implementation of include/ddcb200.h: handle management, per-call host-side preparation of the folded
+// complex taps (float64 -> float32), kernel dispatch, and the chunked double-buffered host path.
+#include "../../include/ddcb200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ddc_kernels.cuh"
+
+using namespace ddck;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t e_ = (expr);                                                                            \
+        if (e_ != cudaSuccess) return fail(DDCB200_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int kNT = 256;       // compute threads per CTA of the fused kernel
+constexpr int kStages = 3;     // TMA pipeline depth
+constexpr int kMaxTapsFused = 2048;
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace
+
+struct ddcb200 {
+    int device = 0;
+    int sm_count = 0;
+    int decim = 1;
+    std::vector<double> taps;       // raw, file order
+    double taps_sum = 0.0;
+    cudaStream_t stream = nullptr;  // compute
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    // device scratch for the generic/short kernels' taps (ring so that back-to-back calls do not race)
+    static constexpr int kRing = 8;
+    float2* d_ctaps[kRing] = {};
+    float2* h_ctaps[kRing] = {};    // pinned
+    cudaEvent_t ring_ev[kRing] = {};
+    int ring_cap = 0, ring_pos = 0;
+    // host-path workspace
+    static constexpr int kBufs = 3;
+    void* d_chunk_in[kBufs] = {};
+    ddcb200_c64* d_chunk_out[kBufs] = {};
+    size_t chunk_in_cap = 0, chunk_out_cap = 0;
+    cudaEvent_t ev_in[kBufs] = {}, ev_k[kBufs] = {}, ev_out[kBufs] = {};
+    int64_t chunk_samples = 1 << 24;
+    int64_t launches = 0;
+    int force_variant = 0;
+    std::string last_variant = "none";
+    bool smem_attr_set = false;
+};
+
+namespace {
+
+// c[k] = taps[T-1-k]/sum * exp(-j 2 pi k step), float64 -> float32; zero padded to n_pad
+void make_ctaps(const ddcb200* h, double step, int n_pad, float2* out) {
+    const int T = (int)h->taps.size();
+    const double fstep = step - std::floor(step);
+    for (int k = 0; k < n_pad; ++k) {
+        if (k < T) {
+            const double hk = h->taps[T - 1 - k] / h->taps_sum;
+            double ph = fstep * (double)k;
+            ph -= std::floor(ph);
+            const double a = -2.0 * M_PI * ph;
+            out[k] = make_float2((float)(hk * std::cos(a)), (float)(hk * std::sin(a)));
+        } else {
+            out[k] = make_float2(0.f, 0.f);
+        }
+    }
+}
+
+unsigned long long to_fx64(double frac01) {
+    // frac01 in [0,1) -> round(frac * 2^64) mod 2^64 using long double (64-bit mantissa on x86)
+    long double v = (long double)frac01 * 18446744073709551616.0L;
+    if (v >= 18446744073709551615.0L) return 0ull;
+    return (unsigned long long)(v + 0.5L);
+}
+
+unsigned long long phase_of(double step, int64_t sample_offset) {
+    // frac(sample_offset * step) * 2^64, exact modular arithmetic on the fixed-point step
+    const double fstep = step - std::floor(step);
+    const unsigned long long sfx = to_fx64(fstep);
+    return (unsigned long long)sample_offset * sfx;
+}
+
+int ensure_ring(ddcb200* h, int n_taps) {
+    if (n_taps <= h->ring_cap) return DDCB200_OK;
+    const int cap = std::max(n_taps, 1024);
+    for (int i = 0; i < ddcb200::kRing; ++i) {
+        if (h->d_ctaps[i]) cudaFree(h->d_ctaps[i]);
+        if (h->h_ctaps[i]) cudaFreeHost(h->h_ctaps[i]);
+        h->d_ctaps[i] = nullptr;
+        h->h_ctaps[i] = nullptr;
+        CUDA_TRY(cudaMalloc(&h->d_ctaps[i], sizeof(float2) * cap));
+        CUDA_TRY(cudaMallocHost(&h->h_ctaps[i], sizeof(float2) * cap));
+        if (!h->ring_ev[i]) CUDA_TRY(cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming));
+    }
+    h->ring_cap = cap;
+    return DDCB200_OK;
+}
+
+template <int D, int R, int MAXT>
+int launch_fused(ddcb200* h, RunParams& p, const float2* ctaps_host, cudaStream_t st, int grid_limit) {
+    using C = FusedCfg<D, R>;
+    auto kern = ddc_fused_kernel<D, R, kNT, kStages, MAXT, false>;
+    const int rows = kNT + p.halo_rows;
+    const size_t smem = 128 + (size_t)kStages * rows * C::PITCH * sizeof(float);
+    if (smem > 227 * 1024) return fail(DDCB200_EINVAL, "fused kernel needs %zu bytes of shared memory", smem);
+    static size_t smem_set[64] = {};  // per device
+    if (h->device < 64 && smem_set[h->device] < smem) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set[h->device] = smem;
+    }
+    TapsParam<MAXT> tp;
+    std::memset(&tp, 0, sizeof(tp));
+    std::memcpy(tp.c2, ctaps_host, sizeof(float2) * (size_t)p.n_taps);
+    const long long grid = std::min<long long>(p.total_tiles, grid_limit);
+    kern<<<(unsigned)grid, kNT + 32, smem, st>>>(p, tp);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    char name[96];
+    snprintf(name, sizeof(name), "fused_tma<D%d,R%d,NT%d,S%d,MAXT%d>", D, R, kNT, kStages, MAXT);
+    h->last_variant = name;
+    return DDCB200_OK;
+}
+
+template <int D, int R>
+int launch_fused_t(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, int grid_limit) {
+    if (p.n_taps <= 512) return launch_fused<D, R, 512>(h, p, ct, st, grid_limit);
+    return launch_fused<D, R, kMaxTapsFused>(h, p, ct, st, grid_limit);
+}
+
+// Core dispatcher for device-resident data.
+int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int64_t n_streams, int64_t in_stride,
+               double step, int64_t sample_offset, ddcb200_c64* d_out, int64_t out_stride, cudaStream_t st,
+               int64_t m_limit = -1) {
+    const int T = (int)h->taps.size();
+    const int D = h->decim;
+    if (!d_in || !d_out) return fail(DDCB200_EINVAL, "null device pointer");
+    if (n_streams <= 0 || n_samples <= 0) return fail(DDCB200_EINVAL, "n_samples and n_streams must be positive");
+    if (n_samples < T) return fail(DDCB200_ETOOSHORT, "n_samples (%lld) < n_taps (%d)", (long long)n_samples, T);
+    if (packed && (n_samples % 4)) return fail(DDCB200_EINVAL, "packed input needs n_samples %% 4 == 0");
+    if (n_streams > 65535) return fail(DDCB200_EINVAL, "at most 65535 streams per call");
+    int64_t M = (n_samples - T) / D + 1;
+    if (m_limit >= 0 && M > m_limit) M = m_limit;
+
+    RunParams p{};
+    p.in = d_in;
+    p.out = reinterpret_cast<float2*>(d_out);
+    p.n_samples = n_samples;
+    p.in_stride = in_stride;
+    p.out_stride = out_stride;
+    p.n_out = M;
+    p.n_streams = (int)n_streams;
+    const double fstep = step - std::floor(step);
+    p.step_fx = to_fx64(fstep);
+    p.phase0_fx = phase_of(step, sample_offset);
+    p.vec_store = ((reinterpret_cast<uintptr_t>(d_out) % 16) == 0 && (out_stride % 2) == 0) ? 1 : 0;
+
+    // ---- fused path eligibility ---------------------------------------------------------------------------
+    int R = 0;
+    switch (D) {
+        case 4: R = 16; break;
+        case 8: R = 8; break;
+        case 16: R = 4; break;
+        case 32: R = 2; break;
+        case 64: R = 1; break;
+        default: R = 0;
+    }
+    long long tiles = 0;
+    int n_taps_pad = T, J = 0, halo_rows = 0;
+    const bool aligned = !packed && (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (in_stride % 4 == 0);
+    if (R > 0 && aligned && h->force_variant != 1) {
+        const int ROW = R * D;
+        J = (T + D - 1) / D;
+        J = ((J + R - 1) / R) * R;  // the tap-block loop is unrolled R times
+        n_taps_pad = J * D;
+        // thread t reads blocks 0 .. J+R-2 of its own row space -> rows t .. t + (J+R-2)/R
+        halo_rows = (J + R - 2) / R;
+        const long long tile_s = (long long)kNT * ROW;
+        const long long need_tail = (long long)halo_rows * ROW;
+        if (n_taps_pad <= kMaxTapsFused && n_samples >= tile_s + need_tail) tiles = (n_samples - need_tail) / tile_s;
+        tiles = std::min<long long>(tiles, M / ((long long)kNT * R));
+        // every output of a full tile must exist: m < M  <=>  m*D + T <= N (true by construction, T <= n_taps_pad)
+    }
+
+    std::vector<float2> ct((size_t)std::max(n_taps_pad, T));
+    make_ctaps(h, step, (int)ct.size(), ct.data());
+
+    int rc = DDCB200_OK;
+    long long m_done = 0;
+    if (tiles > 0) {
+        p.tiles_per_stream = tiles;
+        p.total_tiles = tiles * n_streams;
+        p.n_taps = n_taps_pad;
+        p.n_tap_blocks = J;
+        p.halo_rows = halo_rows;
+        p.m_begin = 0;
+        const int grid_limit = h->sm_count;
+        switch (D) {
+            case 4: rc = launch_fused_t<4, 16>(h, p, ct.data(), st, grid_limit); break;
+            case 8: rc = launch_fused_t<8, 8>(h, p, ct.data(), st, grid_limit); break;
+            case 16: rc = launch_fused_t<16, 4>(h, p, ct.data(), st, grid_limit); break;
+            case 32: rc = launch_fused_t<32, 2>(h, p, ct.data(), st, grid_limit); break;
+            case 64: rc = launch_fused_t<64, 1>(h, p, ct.data(), st, grid_limit); break;
+        }
+        if (rc) return rc;
+        m_done = tiles * (long long)kNT * R;
+    }
+    if (m_done < M) {
+        // stream tails / everything the fused path does not cover
+        rc = ensure_ring(h, T);
+        if (rc) return rc;
+        const int slot = h->ring_pos;
+        h->ring_pos = (h->ring_pos + 1) % ddcb200::kRing;
+        CUDA_TRY(cudaEventSynchronize(h->ring_ev[slot]));  // previous user of this slot has consumed it
+        std::memcpy(h->h_ctaps[slot], ct.data(), sizeof(float2) * T);
+        CUDA_TRY(cudaMemcpyAsync(h->d_ctaps[slot], h->h_ctaps[slot], sizeof(float2) * T, cudaMemcpyHostToDevice, st));
+        p.n_taps = T;
+        p.m_begin = m_done;
+        const long long count = M - m_done;
+        dim3 grid((unsigned)((count + 127) / 128), (unsigned)n_streams);
+        if (packed)
+            ddc_generic_kernel<true><<<grid, 128, 0, st>>>(p, h->d_ctaps[slot], D);
+        else
+            ddc_generic_kernel<false><<<grid, 128, 0, st>>>(p, h->d_ctaps[slot], D);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(h->ring_ev[slot], st));
+        h->launches++;
+        if (tiles == 0) h->last_variant = packed ? "generic<packed10>" : "generic<f32>";
+    }
+    return DDCB200_OK;
+}
+
+int ensure_chunks(ddcb200* h, size_t in_bytes, size_t out_elems) {
+    if (in_bytes > h->chunk_in_cap) {
+        for (int i = 0; i < ddcb200::kBufs; ++i) {
+            if (h->d_chunk_in[i]) cudaFree(h->d_chunk_in[i]);
+            h->d_chunk_in[i] = nullptr;
+            CUDA_TRY(cudaMalloc(&h->d_chunk_in[i], in_bytes));
+        }
+        h->chunk_in_cap = in_bytes;
+    }
+    if (out_elems > h->chunk_out_cap) {
+        for (int i = 0; i < ddcb200::kBufs; ++i) {
+            if (h->d_chunk_out[i]) cudaFree(h->d_chunk_out[i]);
+            h->d_chunk_out[i] = nullptr;
+            CUDA_TRY(cudaMalloc(&h->d_chunk_out[i], out_elems * sizeof(ddcb200_c64)));
+        }
+        h->chunk_out_cap = out_elems;
+    }
+    for (int i = 0; i < ddcb200::kBufs; ++i) {
+        if (!h->ev_in[i]) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+        if (!h->ev_k[i]) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming));
+        if (!h->ev_out[i]) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+    }
+    return DDCB200_OK;
+}
+
+// Host path: every stream is cut into time chunks of `chunk_samples` (+ T-D halo); chunk c of all streams goes
+// H2D on copy_in, through the fused kernel on `stream`, and D2H on copy_out, three buffers deep.
+int run_host(ddcb200* h, const void* h_in, bool packed, int64_t n_samples, int64_t n_streams, int64_t in_stride,
+             double step, int64_t sample_offset, ddcb200_c64* h_out, int64_t out_stride) {
+    const int T = (int)h->taps.size();
+    const int D = h->decim;
+    if (!h_in || !h_out) return fail(DDCB200_EINVAL, "null host pointer");
+    if (n_streams <= 0 || n_samples <= 0) return fail(DDCB200_EINVAL, "n_samples and n_streams must be positive");
+    if (n_samples < T) return fail(DDCB200_ETOOSHORT, "n_samples (%lld) < n_taps (%d)", (long long)n_samples, T);
+    if (packed && (n_samples % 4)) return fail(DDCB200_EINVAL, "packed input needs n_samples %% 4 == 0");
+    const int64_t M = (n_samples - T) / D + 1;
+    // chunk length in outputs; inputs of a chunk start at a multiple of 4*D samples so that packed chunks start on a
+    // byte boundary and float chunks stay 16-byte aligned
+    int64_t per_stream = std::max<int64_t>(h->chunk_samples / n_streams, (int64_t)4 * T);
+    int64_t m_chunk = std::max<int64_t>(per_stream / D, 1);
+    m_chunk = ((m_chunk + 3) / 4) * 4;
+    const int64_t n_chunks = (M + m_chunk - 1) / m_chunk;
+    const int64_t in_chunk_samples = ((m_chunk - 1) * D + T + 3) / 4 * 4;
+    const size_t in_elem_bytes_num = packed ? 5 : 16, in_elem_den = 4;  // bytes per 4 samples
+    const size_t in_row_bytes = (size_t)in_chunk_samples / in_elem_den * in_elem_bytes_num;
+    int rc = ensure_chunks(h, in_row_bytes * (size_t)n_streams + 64, (size_t)m_chunk * (size_t)n_streams);
+    if (rc) return rc;
+
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        const int b = (int)(c % ddcb200::kBufs);
+        const int64_t m0 = c * m_chunk;
+        const int64_t mc = std::min<int64_t>(m_chunk, M - m0);
+        const int64_t n0 = m0 * D;
+        const int64_t nc = (mc - 1) * D + T;                  // samples this chunk needs
+        const int64_t nc4 = std::min<int64_t>((nc + 3) / 4 * 4, n_samples - n0);  // copy whole groups when available
+        const size_t row_bytes = packed ? (size_t)(nc4 / 4 * 5) : (size_t)nc4 * 4;
+        const size_t src_off = packed ? (size_t)(n0 / 4 * 5) : (size_t)n0 * 4;
+        const size_t src_pitch = packed ? (size_t)in_stride : (size_t)in_stride * 4;
+        // buffer b is free once the D2H of chunk c - kBufs finished (ev_out) -- wait on the copy-in stream
+        if (c >= ddcb200::kBufs) CUDA_TRY(cudaStreamWaitEvent(h->copy_in, h->ev_k[b], 0));
+        CUDA_TRY(cudaMemcpy2DAsync(h->d_chunk_in[b], in_row_bytes, reinterpret_cast<const char*>(h_in) + src_off, src_pitch,
+                                   row_bytes, (size_t)n_streams, cudaMemcpyHostToDevice, h->copy_in));
+        CUDA_TRY(cudaEventRecord(h->ev_in[b], h->copy_in));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
+        if (c >= ddcb200::kBufs) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_out[b], 0));
+        const int64_t n_dev = packed ? (nc4 / 4 * 4) : nc;
+        rc = run_device(h, h->d_chunk_in[b], packed, packed ? nc4 : n_dev, n_streams,
+                        packed ? (int64_t)in_row_bytes : (int64_t)(in_row_bytes / 4), step, sample_offset + n0,
+                        h->d_chunk_out[b], m_chunk, h->stream, mc);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev_k[b], h->stream));
+        CUDA_TRY(cudaStreamWaitEvent(h->copy_out, h->ev_k[b], 0));
+        CUDA_TRY(cudaMemcpy2DAsync(h_out + m0, (size_t)out_stride * sizeof(ddcb200_c64), h->d_chunk_out[b],
+                                   (size_t)m_chunk * sizeof(ddcb200_c64), (size_t)mc * sizeof(ddcb200_c64), (size_t)n_streams,
+                                   cudaMemcpyDeviceToHost, h->copy_out));
+        CUDA_TRY(cudaEventRecord(h->ev_out[b], h->copy_out));
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->copy_out));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->copy_in));
+    return DDCB200_OK;
+}
+
+}  // namespace
+
+// ================================================================================================================
+extern "C" {
+
+int ddcb200_version(void) { return DDCB200_VERSION; }
+const char* ddcb200_last_error(void) { return g_err; }
+
+int64_t ddcb200_out_len(int64_t n_samples, int n_taps, int decimation) {
+    if (n_samples <= 0 || n_taps <= 0 || decimation <= 0) return 0;
+    const int64_t full = (n_samples >= n_taps ? n_samples - n_taps : n_taps - n_samples) + 1;
+    return (full + decimation - 1) / decimation;
+}
+
+int ddcb200_set_taps(ddcb200_t* h, const double* taps, int n_taps) {
+    if (!h || !taps || n_taps <= 0) return fail(DDCB200_EINVAL, "set_taps: bad arguments");
+    double s = 0.0;
+    for (int i = 0; i < n_taps; ++i) s += taps[i];  // same left-to-right float64 sum as Python's sum() (ddc.py:98)
+    if (!(s != 0.0) || !std::isfinite(s)) return fail(DDCB200_EINVAL, "set_taps: sum of taps is %g", s);
+    h->taps.assign(taps, taps + n_taps);
+    h->taps_sum = s;
+    return DDCB200_OK;
+}
+
+int ddcb200_set_decimation(ddcb200_t* h, int decimation) {
+    if (!h || decimation <= 0) return fail(DDCB200_EINVAL, "set_decimation: bad arguments");
+    h->decim = decimation;
+    return DDCB200_OK;
+}
+
+int ddcb200_create(ddcb200_t** handle, int device, const double* taps, int n_taps, int decimation) {
+    if (!handle) return fail(DDCB200_EINVAL, "create: null handle pointer");
+    *handle = nullptr;
+    if (!taps || n_taps <= 0 || decimation <= 0) return fail(DDCB200_EINVAL, "create: bad taps/decimation");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(DDCB200_EINVAL, "create: device %d of %d", device, ndev);
+    DeviceGuard g(device);
+    if (!g.ok) return fail(DDCB200_ECUDA, "create: cannot select device %d", device);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(DDCB200_ECUDA, "create: device %d is sm_%d%d; this library is sm_100a only", device, prop.major, prop.minor);
+    ddcb200* h = new (std::nothrow) ddcb200();
+    if (!h) return fail(DDCB200_ENOMEM, "create: out of memory");
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    int rc = ddcb200_set_taps(h, taps, n_taps);
+    if (!rc) rc = ddcb200_set_decimation(h, decimation);
+    if (rc) {
+        delete h;
+        return rc;
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete h;
+        return fail(DDCB200_ECUDA, "create: stream creation failed: %s", cudaGetErrorString(e));
+    }
+    *handle = h;
+    return DDCB200_OK;
+}
+
+void ddcb200_destroy(ddcb200_t* h) {
+    if (!h) return;
+    DeviceGuard g(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < ddcb200::kRing; ++i) {
+        if (h->d_ctaps[i]) cudaFree(h->d_ctaps[i]);
+        if (h->h_ctaps[i]) cudaFreeHost(h->h_ctaps[i]);
+        if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
+    }
+    for (int i = 0; i < ddcb200::kBufs; ++i) {
+        if (h->d_chunk_in[i]) cudaFree(h->d_chunk_in[i]);
+        if (h->d_chunk_out[i]) cudaFree(h->d_chunk_out[i]);
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]);
+        if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+    }
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_in) cudaStreamDestroy(h->copy_in);
+    if (h->copy_out) cudaStreamDestroy(h->copy_out);
+    delete h;
+}
+
+int ddcb200_run_f32(ddcb200_t* h, const float* d_in, int64_t n_samples, int64_t n_streams, int64_t in_stride,
+                    double step, int64_t sample_offset, ddcb200_c64* d_out, int64_t out_stride, void* cuda_stream) {
+    if (!h) return fail(DDCB200_EINVAL, "null handle");
+    DeviceGuard g(h->device);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    return run_device(h, d_in, false, n_samples, n_streams, in_stride, step, sample_offset, d_out, out_stride, st);
+}
+
+int ddcb200_run_packed10(ddcb200_t* h, const uint8_t* d_in, int64_t n_samples, int64_t n_streams, int64_t in_stride_bytes,
+                         double step, int64_t sample_offset, ddcb200_c64* d_out, int64_t out_stride, void* cuda_stream) {
+    if (!h) return fail(DDCB200_EINVAL, "null handle");
+    DeviceGuard g(h->device);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    return run_device(h, d_in, true, n_samples, n_streams, in_stride_bytes, step, sample_offset, d_out, out_stride, st);
+}
+
+int ddcb200_unpack10(ddcb200_t* h, const uint8_t* d_in, int64_t n_samples, int16_t* o16, float* of32, void* cuda_stream) {
+    if (!h || !d_in) return fail(DDCB200_EINVAL, "unpack10: bad arguments");
+    if (n_samples < 0 || (n_samples % 4)) return fail(DDCB200_EINVAL, "unpack10: n_samples must be a multiple of 4");
+    if (n_samples == 0) return DDCB200_OK;
+    DeviceGuard g(h->device);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    const long long groups = n_samples / 4;
+    unpack10_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(d_in, groups, o16, of32);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return DDCB200_OK;
+}
+
+int ddcb200_run_short_f32(ddcb200_t* h, const float* d_in, int64_t n_samples, double step, int64_t sample_offset,
+                          ddcb200_c64* d_out, void* cuda_stream) {
+    if (!h || !d_in || !d_out) return fail(DDCB200_EINVAL, "run_short: bad arguments");
+    const int T = (int)h->taps.size();
+    if (n_samples <= 0 || n_samples >= T) return fail(DDCB200_EINVAL, "run_short: needs 0 < n_samples < n_taps");
+    DeviceGuard g(h->device);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    int rc = ensure_ring(h, T);
+    if (rc) return rc;
+    const int slot = h->ring_pos;
+    h->ring_pos = (h->ring_pos + 1) % ddcb200::kRing;
+    CUDA_TRY(cudaEventSynchronize(h->ring_ev[slot]));
+    float* hh = reinterpret_cast<float*>(h->h_ctaps[slot]);
+    for (int i = 0; i < T; ++i) hh[i] = (float)(h->taps[i] / h->taps_sum);
+    CUDA_TRY(cudaMemcpyAsync(h->d_ctaps[slot], hh, sizeof(float) * T, cudaMemcpyHostToDevice, st));
+    RunParams p{};
+    p.in = d_in;
+    p.out = reinterpret_cast<float2*>(d_out);
+    p.n_samples = n_samples;
+    p.n_out = ddcb200_out_len(n_samples, T, h->decim);
+    const double fstep = step - std::floor(step);
+    p.step_fx = to_fx64(fstep);
+    p.phase0_fx = phase_of(step, sample_offset);
+    ddc_short_kernel<<<(unsigned)((p.n_out + 63) / 64), 64, 0, st>>>(p, reinterpret_cast<const float*>(h->d_ctaps[slot]), T, h->decim);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(h->ring_ev[slot], st));
+    h->launches++;
+    h->last_variant = "short<f32>";
+    return DDCB200_OK;
+}
+
+int ddcb200_run_host_f32(ddcb200_t* h, const float* h_in, int64_t n_samples, int64_t n_streams, int64_t in_stride,
+                         double step, int64_t sample_offset, ddcb200_c64* h_out, int64_t out_stride) {
+    if (!h) return fail(DDCB200_EINVAL, "null handle");
+    DeviceGuard g(h->device);
+    const int T = (int)h->taps.size();
+    if (n_samples > 0 && n_samples < T) {
+        if (n_streams != 1) return fail(DDCB200_ETOOSHORT, "n_samples < n_taps is only supported for a single stream");
+        if (!h_in || !h_out) return fail(DDCB200_EINVAL, "null host pointer");
+        const int64_t m = ddcb200_out_len(n_samples, T, h->decim);
+        int rc = ensure_chunks(h, (size_t)T * 4, (size_t)m);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h->d_chunk_in[0], h_in, (size_t)n_samples * 4, cudaMemcpyHostToDevice, h->stream));
+        rc = ddcb200_run_short_f32(h, reinterpret_cast<const float*>(h->d_chunk_in[0]), n_samples, step, sample_offset,
+                                   h->d_chunk_out[0], h->stream);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h_out, h->d_chunk_out[0], (size_t)m * sizeof(ddcb200_c64), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        return DDCB200_OK;
+    }
+    return run_host(h, h_in, false, n_samples, n_streams, in_stride, step, sample_offset, h_out, out_stride);
+}
+
+int ddcb200_run_host_packed10(ddcb200_t* h, const uint8_t* h_in, int64_t n_samples, int64_t n_streams,
+                              int64_t in_stride_bytes, double step, int64_t sample_offset, ddcb200_c64* h_out,
+                              int64_t out_stride) {
+    if (!h) return fail(DDCB200_EINVAL, "null handle");
+    DeviceGuard g(h->device);
+    return run_host(h, h_in, true, n_samples, n_streams, in_stride_bytes, step, sample_offset, h_out, out_stride);
+}
+
+void* ddcb200_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        fail(DDCB200_ENOMEM, "host_alloc(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+void ddcb200_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int ddcb200_sync(ddcb200_t* h) {
+    if (!h) return fail(DDCB200_EINVAL, "null handle");
+    DeviceGuard g(h->device);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return DDCB200_OK;
+}
+void* ddcb200_stream(ddcb200_t* h) { return h ? (void*)h->stream : nullptr; }
+int64_t ddcb200_launch_count(ddcb200_t* h) { return h ? h->launches : 0; }
+const char* ddcb200_last_variant(ddcb200_t* h) { return h ? h->last_variant.c_str() : "none"; }
+
+int ddcb200_set_option(ddcb200_t* h, const char* key, int64_t value) {
+    if (!h || !key) return fail(DDCB200_EINVAL, "set_option: bad arguments");
+    if (!strcmp(key, "variant")) {
+        h->force_variant = (int)value;
+        return DDCB200_OK;
+    }
+    if (!strcmp(key, "chunk_samples")) {
+        if (value < 1024) return fail(DDCB200_EINVAL, "chunk_samples too small");
+        h->chunk_samples = value;
+        return DDCB200_OK;
+    }
+    return fail(DDCB200_EINVAL, "unknown option '%s'", key);
+}
+
+}  // extern "C"

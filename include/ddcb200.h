@@ -1,0 +1,129 @@
+/*
+ * ddcb200.h -- C ABI of the B200-native fused digital down-converter (NCO mix -> FIR -> decimate).
+ *
+ * This is the drop-in boundary for the feng/ddc hot path of ska-sa/dc_sand.  The reference has no FFI layer
+ * of its own: its boundary is the Python class feng/ddc/src/ddc.py:10-188.  Each entry point below names the
+ * reference interface it replaces (paths relative to the reference checkout).  Plain pointers and sizes only;
+ * no C++ or torch types cross this boundary; no exceptions: every function returns 0 on success or a negative
+ * DDCB200_E* code and records a message retrievable with ddcb200_last_error().
+ *
+ * Arithmetic contract (reference: feng/ddc/src/cwg.py:31-36, ddc.py:66,98,119):
+ *
+ *     y[s][m] = rot(m) * sum_{k=0}^{T-1} c[k] * x[s][m*D + k]            m = 0 .. M-1,  M = (N-T)/D + 1
+ *     c[k]    = taps[T-1-k] / sum(taps) * exp(-j 2 pi k step)           (float64 on the host, then float32)
+ *     rot(m)  = exp(-j 2 pi frac((sample_offset + m*D) * step))          (64-bit fixed-point phase on device)
+ *
+ * which equals the reference's  convolve(x * exp(-j 2 pi n step), taps, "valid") / sum(taps) [0::D]  with
+ * `step` = phase_step_cycles = int(N*fc/fs)/(N-1) computed by the caller exactly as cwg.py:31-33 does.
+ * Accumulation is FP32 FMA on CUDA cores; output is interleaved (re, im) float32 ("complex64"), the layout of
+ * the reference's own GPU prototype (feng/ddc/src/ddc_host_gpu.py:51,136).
+ */
+#ifndef DDCB200_H_
+#define DDCB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDCB200_VERSION 100 /* 0.1.0 */
+
+/* status codes */
+#define DDCB200_OK 0
+#define DDCB200_EINVAL (-1)   /* bad argument (NULL, non-positive size, misaligned pointer ...) */
+#define DDCB200_ECUDA (-2)    /* a CUDA runtime call or kernel failed; see ddcb200_last_error() */
+#define DDCB200_ENOMEM (-3)   /* host or device allocation failed */
+#define DDCB200_ETOOSHORT (-4) /* n_samples < n_taps on an entry point that needs N >= T */
+
+typedef struct ddcb200 ddcb200_t;
+
+/* complex64 element of the output, interleaved re/im float32 (ddc_host_gpu.py:51,136). */
+typedef struct ddcb200_c64 {
+    float re, im;
+} ddcb200_c64;
+
+/* ---- lifetime --------------------------------------------------------------------------------------------
+ * Replaces DigitalDownConverter.__init__ (ddc.py:13-31) minus the CSV parsing, which stays in Python
+ * (_import_ddc_filter_coeffs, ddc.py:33-48).  `taps` are the raw float64 coefficients in file order; the
+ * library normalises by their float64 sum (ddc.py:98).  One handle is bound to one CUDA device and owns one
+ * non-blocking CUDA stream plus a small workspace.  Handles are independent; calls on one handle must not
+ * overlap in time (same rule as the reference object, which is not thread-safe either). */
+int ddcb200_create(ddcb200_t** handle, int device, const double* taps, int n_taps, int decimation);
+void ddcb200_destroy(ddcb200_t* handle);
+
+/* Runtime coefficient reload (the reference re-reads a CSV into a new object; ddc.py:33-48). */
+int ddcb200_set_taps(ddcb200_t* handle, const double* taps, int n_taps);
+int ddcb200_set_decimation(ddcb200_t* handle, int decimation);
+
+/* Output length of run(): ceil((|N - T| + 1) / D); scipy's "valid" convolution swaps operands when N < T
+ * (ddc.py:98,119).  Returns 0 for n_samples <= 0. */
+int64_t ddcb200_out_len(int64_t n_samples, int n_taps, int decimation);
+
+/* ---- device-resident entry points (inputs and outputs already in HBM) ------------------------------------
+ * Replace _mix + _bandpass_fir_filter + _decimate (ddc.py:51-66, 85-100, 102-119) and the NCO generation of
+ * cwg.generate_carrier_wave(complex=True) (cwg.py:31-36) for `n_streams` independent 1-D streams.
+ *   d_in               device pointer; stream s starts at d_in + s * in_stride (elements: float32 samples)
+ *   n_samples          N per stream (>= n_taps, else DDCB200_ETOOSHORT -- see ddcb200_run_short_f32)
+ *   phase_step_cycles  NCO cycles per sample, int(N*fc/fs)/(N-1) for a one-shot call (cwg.py:31-33)
+ *   sample_offset      index of x[0] within the logical stream (chunked operation); 0 for a one-shot call
+ *   d_out              device pointer to complex64; stream s at d_out + s * out_stride; M elements each
+ *   cuda_stream        cudaStream_t to launch on, or NULL for the handle's own stream
+ * Asynchronous: returns after enqueueing.  Use ddcb200_sync() (or your own stream sync) before reading. */
+int ddcb200_run_f32(ddcb200_t* handle, const float* d_in, int64_t n_samples, int64_t n_streams,
+                    int64_t in_stride, double phase_step_cycles, int64_t sample_offset, ddcb200_c64* d_out,
+                    int64_t out_stride, void* cuda_stream);
+
+/* Same, with the digitiser's packed 10-bit transport format fused into the load path.  Replaces the stub
+ * _decode_8bit_to_10bit_to_float_data (ddc.py:68-83) + the three stages above.  Format (defined by this
+ * library): sample k is a two's-complement 10-bit integer, MSB first, at bit offset 10*k of a
+ * big-endian bit stream; 4 samples per 5 bytes.  `in_stride_bytes` separates streams; n_samples must be a
+ * multiple of 4. */
+int ddcb200_run_packed10(ddcb200_t* handle, const uint8_t* d_in, int64_t n_samples, int64_t n_streams,
+                         int64_t in_stride_bytes, double phase_step_cycles, int64_t sample_offset,
+                         ddcb200_c64* d_out, int64_t out_stride, void* cuda_stream);
+
+/* Stand-alone unpack stage (ddc.py:68-83), bit-exact integer work: packed bytes -> int16 and/or float32
+ * (either output pointer may be NULL). */
+int ddcb200_unpack10(ddcb200_t* handle, const uint8_t* d_in, int64_t n_samples, int16_t* d_out_i16,
+                     float* d_out_f32, void* cuda_stream);
+
+/* N < T corner of the reference: scipy swaps the operands, so run() returns
+ *     y[i] = (1/sum(taps)) * sum_n mix[n] * taps[i*D' ... ]   -- precisely: full[i] = sum_n mix[n]*taps[i+N-1-n],
+ * i = 0..T-N, then [0::D].  Kept for drop-in fidelity (ddc.py:98 with len(mix) < len(taps)); single stream. */
+int ddcb200_run_short_f32(ddcb200_t* handle, const float* d_in, int64_t n_samples, double phase_step_cycles,
+                          int64_t sample_offset, ddcb200_c64* d_out, void* cuda_stream);
+
+/* ---- host-buffer entry points (what DigitalDownConverter.run binds to) -------------------------------------
+ * Replace DigitalDownConverter.run (ddc.py:121-188) for host arrays: time-chunked, double-buffered
+ * H2D -> fused kernel -> D2H on two CUDA streams, synchronous on return.  Pinned host memory (see
+ * ddcb200_host_alloc) makes the copies truly asynchronous; pageable memory works but is slower.
+ * N < T is routed to the short path when n_streams == 1, else DDCB200_ETOOSHORT. */
+int ddcb200_run_host_f32(ddcb200_t* handle, const float* h_in, int64_t n_samples, int64_t n_streams,
+                         int64_t in_stride, double phase_step_cycles, int64_t sample_offset,
+                         ddcb200_c64* h_out, int64_t out_stride);
+int ddcb200_run_host_packed10(ddcb200_t* handle, const uint8_t* h_in, int64_t n_samples, int64_t n_streams,
+                              int64_t in_stride_bytes, double phase_step_cycles, int64_t sample_offset,
+                              ddcb200_c64* h_out, int64_t out_stride);
+
+/* Pinned host memory helpers (the reference's prototype uses cuda.pagelocked_empty, ddc_host_gpu.py:45-58). */
+void* ddcb200_host_alloc(size_t bytes);
+void ddcb200_host_free(void* p);
+
+/* ---- misc ------------------------------------------------------------------------------------------------ */
+int ddcb200_sync(ddcb200_t* handle);            /* waits for the handle's own stream */
+void* ddcb200_stream(ddcb200_t* handle);        /* the handle's cudaStream_t */
+const char* ddcb200_last_error(void);           /* thread-local message of the last failure */
+int ddcb200_version(void);
+/* Number of kernels of this library launched through `handle` so far (bench.py's gpu_launches). */
+int64_t ddcb200_launch_count(ddcb200_t* handle);
+/* Name of the kernel variant the last run on this handle dispatched to (e.g. "fused_tma<D16,R4,T256>"). */
+const char* ddcb200_last_variant(ddcb200_t* handle);
+/* Tuning/diagnostic knobs: "variant" (0 = auto, 1 = force generic kernel), "chunk_samples" (host path). */
+int ddcb200_set_option(ddcb200_t* handle, const char* key, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDCB200_H_ */
