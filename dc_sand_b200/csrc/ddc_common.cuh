@@ -30,6 +30,7 @@ struct RunParams {
     int halo_rows;               // extra rows staged behind each tile
     int n_streams;
     int vec_store;               // 1 if out pointer / stride allow 16-byte stores
+    int debug_mode;              // 0 normal; 1 compute only (no TMA, no waits); 2 memory only (no FIR) -- ceilings for tuning
 };
 
 // ---- NCO: exp(-j 2 pi ph / 2^64) from a 64-bit fixed-point phase ------------------------------------------
@@ -125,9 +126,29 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+#ifndef DDCB200_PIN_FFMA2_ORDER
+#define DDCB200_PIN_FFMA2_ORDER 1
+#endif
 __device__ __forceinline__ float2 ffma2(float x, float2 t, float2 acc) {
-    // acc(re,im) += x * t(re,im); the compiler emits FFMA2 Racc, Rx.F32 (broadcast), URt.F32x2, Racc
+    // acc(re,im) += x * t(re,im); SASS: FFMA2 Racc, Rx.F32 (broadcast), URt.F32x2, Racc
+#if DDCB200_PIN_FFMA2_ORDER
+    // volatile asm keeps the source order of the FMAs (tap-major, R independent accumulator chains round-robin):
+    // left alone, the scheduler interleaves only two chains and the 2-cycle FFMA2 issue cadence exposes its latency.
+    asm volatile(
+        "{\n"
+        ".reg .b64 xx, tt, aa;\n"
+        "mov.b64 xx, {%2, %2};\n"
+        "mov.b64 tt, {%3, %4};\n"
+        "mov.b64 aa, {%0, %1};\n"
+        "fma.rn.f32x2 aa, xx, tt, aa;\n"
+        "mov.b64 {%0, %1}, aa;\n"
+        "}\n"
+        : "+f"(acc.x), "+f"(acc.y)
+        : "f"(x), "f"(t.x), "f"(t.y));
+    return acc;
+#else
     return __ffma2_rn(make_float2(x, x), t, acc);
+#endif
 }
 
 }  // namespace ddck

@@ -35,8 +35,8 @@ int fail(int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(DDCB200_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-constexpr int kNT = 256;       // compute threads per CTA of the fused kernel
 constexpr int kStages = 3;     // TMA pipeline depth
+constexpr int kS = 32;         // thread-rows per TMA bulk copy (super-row)
 constexpr int kMaxTapsFused = 2048;
 
 struct DeviceGuard {
@@ -76,6 +76,7 @@ struct ddcb200 {
     int64_t chunk_samples = 1 << 24;
     int64_t launches = 0;
     int force_variant = 0;
+    int debug_mode = 0;
     std::string last_variant = "none";
     bool smem_attr_set = false;
 };
@@ -129,12 +130,11 @@ int ensure_ring(ddcb200* h, int n_taps) {
     return DDCB200_OK;
 }
 
-template <int D, int R, int MAXT>
+template <int D, int R, int KS, int MAXT>
 int launch_fused(ddcb200* h, RunParams& p, const float2* ctaps_host, cudaStream_t st, int grid_limit) {
-    using C = FusedCfg<D, R>;
-    auto kern = ddc_fused_kernel<D, R, kNT, kStages, MAXT, false>;
-    const int rows = kNT + p.halo_rows;
-    const size_t smem = 128 + (size_t)kStages * rows * C::PITCH * sizeof(float);
+    using C = FusedCfg<D, R, kS, KS>;
+    auto kern = ddc_fused_kernel<D, R, kS, KS, kStages, MAXT, false>;
+    const size_t smem = 128 + C::XBUF_BYTES + (size_t)kStages * C::stage_floats(p.halo_rows) * sizeof(float);
     if (smem > 227 * 1024) return fail(DDCB200_EINVAL, "fused kernel needs %zu bytes of shared memory", smem);
     static size_t smem_set[64] = {};  // per device
     if (h->device < 64 && smem_set[h->device] < smem) {
@@ -145,19 +145,25 @@ int launch_fused(ddcb200* h, RunParams& p, const float2* ctaps_host, cudaStream_
     std::memset(&tp, 0, sizeof(tp));
     std::memcpy(tp.c2, ctaps_host, sizeof(float2) * (size_t)p.n_taps);
     const long long grid = std::min<long long>(p.total_tiles, grid_limit);
-    kern<<<(unsigned)grid, kNT + 32, smem, st>>>(p, tp);
+    kern<<<(unsigned)grid, C::NT + 32, smem, st>>>(p, tp);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
     char name[96];
-    snprintf(name, sizeof(name), "fused_tma<D%d,R%d,NT%d,S%d,MAXT%d>", D, R, kNT, kStages, MAXT);
+    snprintf(name, sizeof(name), "fused_tma<D%d,R%d,S%d,KS%d,STAGES%d,MAXT%d>", D, R, kS, KS, kStages, MAXT);
     h->last_variant = name;
     return DDCB200_OK;
 }
 
 template <int D, int R>
-int launch_fused_t(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, int grid_limit) {
-    if (p.n_taps <= 512) return launch_fused<D, R, 512>(h, p, ct, st, grid_limit);
-    return launch_fused<D, R, kMaxTapsFused>(h, p, ct, st, grid_limit);
+int launch_fused_t(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, int grid_limit, int ks) {
+    if constexpr (R <= 4) {  // larger R: exchange buffer / register budget do not fit 544 threads
+        if (ks == 2) {
+            if (p.n_taps <= 512) return launch_fused<D, R, 2, 512>(h, p, ct, st, grid_limit);
+            return launch_fused<D, R, 2, kMaxTapsFused>(h, p, ct, st, grid_limit);
+        }
+    }
+    if (p.n_taps <= 512) return launch_fused<D, R, 1, 512>(h, p, ct, st, grid_limit);
+    return launch_fused<D, R, 1, kMaxTapsFused>(h, p, ct, st, grid_limit);
 }
 
 // Core dispatcher for device-resident data.
@@ -186,6 +192,7 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
     p.step_fx = to_fx64(fstep);
     p.phase0_fx = phase_of(step, sample_offset);
     p.vec_store = ((reinterpret_cast<uintptr_t>(d_out) % 16) == 0 && (out_stride % 2) == 0) ? 1 : 0;
+    p.debug_mode = h->debug_mode;
 
     // ---- fused path eligibility ---------------------------------------------------------------------------
     int R = 0;
@@ -198,20 +205,20 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         default: R = 0;
     }
     long long tiles = 0;
-    int n_taps_pad = T, J = 0, halo_rows = 0;
+    int n_taps_pad = T, J = 0, halo_rows = 0, ks = 1;
     const bool aligned = !packed && (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (in_stride % 4 == 0);
     if (R > 0 && aligned && h->force_variant != 1) {
-        const int ROW = R * D;
         J = (T + D - 1) / D;
-        J = ((J + R - 1) / R) * R;  // the tap-block loop is unrolled R times
+        // tap split 2 (16 compute warps) whenever it costs no extra zero taps; option "variant" 2 / 3 force KS 1 / 2
+        ks = (J % (2 * R) == 0 && R <= 4) ? 2 : 1;
+        if (h->force_variant == 2) ks = 1;
+        if (h->force_variant == 3 && R <= 4) ks = 2;
+        J = ((J + ks * R - 1) / (ks * R)) * (ks * R);  // each thread's tap-block loop is unrolled R times
         n_taps_pad = J * D;
-        // thread t reads blocks 0 .. J+R-2 of its own row space -> rows t .. t + (J+R-2)/R
+        // a thread-row reads blocks 0 .. J+R-2 of its own row space -> rows g .. g + (J+R-2)/R
         halo_rows = (J + R - 2) / R;
-        const long long tile_s = (long long)kNT * ROW;
-        const long long need_tail = (long long)halo_rows * ROW;
-        if (n_taps_pad <= kMaxTapsFused && n_samples >= tile_s + need_tail) tiles = (n_samples - need_tail) / tile_s;
-        tiles = std::min<long long>(tiles, M / ((long long)kNT * R));
-        // every output of a full tile must exist: m < M  <=>  m*D + T <= N (true by construction, T <= n_taps_pad)
+        const long long tile_out = 256LL * R;
+        if (n_taps_pad <= kMaxTapsFused) tiles = (M + tile_out - 1) / tile_out;  // the last one may be ragged
     }
 
     std::vector<float2> ct((size_t)std::max(n_taps_pad, T));
@@ -228,14 +235,14 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         p.m_begin = 0;
         const int grid_limit = h->sm_count;
         switch (D) {
-            case 4: rc = launch_fused_t<4, 16>(h, p, ct.data(), st, grid_limit); break;
-            case 8: rc = launch_fused_t<8, 8>(h, p, ct.data(), st, grid_limit); break;
-            case 16: rc = launch_fused_t<16, 4>(h, p, ct.data(), st, grid_limit); break;
-            case 32: rc = launch_fused_t<32, 2>(h, p, ct.data(), st, grid_limit); break;
-            case 64: rc = launch_fused_t<64, 1>(h, p, ct.data(), st, grid_limit); break;
+            case 4: rc = launch_fused_t<4, 16>(h, p, ct.data(), st, grid_limit, ks); break;
+            case 8: rc = launch_fused_t<8, 8>(h, p, ct.data(), st, grid_limit, ks); break;
+            case 16: rc = launch_fused_t<16, 4>(h, p, ct.data(), st, grid_limit, ks); break;
+            case 32: rc = launch_fused_t<32, 2>(h, p, ct.data(), st, grid_limit, ks); break;
+            case 64: rc = launch_fused_t<64, 1>(h, p, ct.data(), st, grid_limit, ks); break;
         }
         if (rc) return rc;
-        m_done = tiles * (long long)kNT * R;
+        m_done = M;
     }
     if (m_done < M) {
         // stream tails / everything the fused path does not cover
@@ -546,6 +553,10 @@ int ddcb200_set_option(ddcb200_t* h, const char* key, int64_t value) {
     if (!h || !key) return fail(DDCB200_EINVAL, "set_option: bad arguments");
     if (!strcmp(key, "variant")) {
         h->force_variant = (int)value;
+        return DDCB200_OK;
+    }
+    if (!strcmp(key, "debug_mode")) {
+        h->debug_mode = (int)value;
         return DDCB200_OK;
     }
     if (!strcmp(key, "chunk_samples")) {

@@ -24,6 +24,13 @@ from . import _lib, cwg
 _log = logging.getLogger(__name__)
 
 
+def _torch_stream(torch, device):
+    """cudaStream_t of torch's current stream.  torch's default stream is the legacy NULL stream, but NULL means "the
+    handle's own stream" in the C ABI, so it is passed as cudaStreamLegacy (0x1)."""
+    st = torch.cuda.current_stream(device).cuda_stream
+    return st if st else 1
+
+
 class DigitalDownConverter:
     """Digital Down Conversion (reference: ddc.py:10)."""
 
@@ -173,7 +180,7 @@ class DigitalDownConverter:
         dev = torch.device("cuda", self.device)
         d_in = torch.from_numpy(p).to(dev)
         d_out = torch.empty(n, dtype=torch.float32, device=dev)
-        st = torch.cuda.current_stream(dev).cuda_stream
+        st = _torch_stream(torch, dev)
         _lib.check(_lib.load().ddcb200_unpack10(self._get_handle(), d_in.data_ptr(), n, None, d_out.data_ptr(), st))
         return d_out.cpu().numpy()
 
@@ -247,7 +254,7 @@ class DigitalDownConverter:
         out2 = out.unsqueeze(0) if out.dim() == 1 else out
         if out2.shape != (s, m) or out2.dtype != torch.complex64 or out2.stride(1) != 1:
             raise ValueError("out must be complex64 [streams, M] with contiguous rows")
-        st = torch.cuda.current_stream(x.device).cuda_stream
+        st = _torch_stream(torch, x.device)
         lib = _lib.load()
         fn = lib.ddcb200_run_packed10 if packed else lib.ddcb200_run_f32
         _lib.check(

@@ -118,11 +118,36 @@ __global__ void k_ffma2_ldcu(float* out, Res* res, float a) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0) res[blockIdx.x].cyc = t1 - t0;
 }
+// (e2) as (e) but two taps per LDCU.128
+template <int NACC>
+__global__ void k_ffma2_ldcu128(float* out, Res* res, float a) {
+    float2 acc[NACC]; float x[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) { acc[i] = make_float2(0.f, 0.f); x[i] = threadIdx.x * 0.001f + i * a; }
+    const float4* t4 = reinterpret_cast<const float4*>(ctaps);
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITERS; ++it) {
+        const int base = (it & 15) * (32 / NACC);
+#pragma unroll
+        for (int u = 0; u < 32 / NACC; ++u) {
+            float4 t = t4[base + u];
+#pragma unroll
+            for (int i = 0; i < NACC; ++i) acc[i] = __ffma2_rn(make_float2(x[i], x[i]), make_float2(t.x, t.y), acc[i]);
+#pragma unroll
+            for (int i = 0; i < NACC; ++i) acc[i] = __ffma2_rn(make_float2(x[i], x[i]), make_float2(t.z, t.w), acc[i]);
+        }
+    }
+    long long t1 = clock64();
+    float s = 0; for (int i = 0; i < NACC; ++i) s += acc[i].x + acc[i].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) res[blockIdx.x].cyc = t1 - t0;
+}
 // (f) as (e, NACC=4) plus one LDS.128 of fresh samples per LDSPER taps (x rotates) — smem issue + bandwidth interplay
 template <int NACC, int TAPS_PER_LDS>
 __global__ void k_ffma2_ldcu_lds(float* out, Res* res, float a) {
     extern __shared__ float4 sm[];
-    for (int i = threadIdx.x; i < 4096; i += blockDim.x) sm[i] = make_float4(a * i, a, 1.f, 2.f);
+    for (int i = threadIdx.x; i < 17 * (int)blockDim.x + 16; i += blockDim.x) sm[i] = make_float4(a * i, a, 1.f, 2.f);
     __syncthreads();
     float2 acc[NACC]; float4 xv = sm[threadIdx.x];
 #pragma unroll
@@ -172,9 +197,9 @@ int main() {
     CK(cudaMalloc(&d_out, sizeof(float) * nsm * 8 * 1024)); CK(cudaMalloc(&d_res, sizeof(Res) * nsm * 8));
     std::vector<float2> h(2048); for (int i = 0; i < 2048; ++i) h[i] = make_float2(1e-3f * i, -1e-3f * i);
     CK(cudaMemcpyToSymbol(ctaps, h.data(), sizeof(float2) * 2048));
-    CK(cudaFuncSetAttribute(k_ffma2_ldcu_lds<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-    CK(cudaFuncSetAttribute(k_ffma2_ldcu_lds<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-    CK(cudaFuncSetAttribute(k_ffma2_ldcu_lds<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    CK(cudaFuncSetAttribute(k_ffma2_ldcu_lds<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
+    CK(cudaFuncSetAttribute(k_ffma2_ldcu_lds<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
+    CK(cudaFuncSetAttribute(k_ffma2_ldcu_lds<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200000));
     const int blocks[] = {128, 256, 512, 1024};
     for (int b : blocks) {
         int grid = nsm;
@@ -187,11 +212,14 @@ int main() {
         run("ffma2_ldcu<1> (1 tap/FFMA2)", [&] { k_ffma2_ldcu<1><<<grid, b>>>(d_out, d_res, 0.5f); }, grid, b, (double)ITERS * 128, d_out, d_res);
         run("ffma2_ldcu<2>", [&] { k_ffma2_ldcu<2><<<grid, b>>>(d_out, d_res, 0.5f); }, grid, b, (double)ITERS * 128, d_out, d_res);
         run("ffma2_ldcu<4>", [&] { k_ffma2_ldcu<4><<<grid, b>>>(d_out, d_res, 0.5f); }, grid, b, (double)ITERS * 128, d_out, d_res);
+        run("ffma2_ldcu128<1> (2 taps/LDCU.128, 2 FFMA2)", [&] { k_ffma2_ldcu128<1><<<grid, b>>>(d_out, d_res, 0.5f); }, grid, b, (double)ITERS * 128, d_out, d_res);
+        run("ffma2_ldcu128<2> (4 FFMA2 per LDCU.128)", [&] { k_ffma2_ldcu128<2><<<grid, b>>>(d_out, d_res, 0.5f); }, grid, b, (double)ITERS * 128, d_out, d_res);
+        run("ffma2_ldcu128<4> (8 FFMA2 per LDCU.128)", [&] { k_ffma2_ldcu128<4><<<grid, b>>>(d_out, d_res, 0.5f); }, grid, b, (double)ITERS * 128, d_out, d_res);
         run("ffma2_ldcu<8>", [&] { k_ffma2_ldcu<8><<<grid, b>>>(d_out, d_res, 0.5f); }, grid, b, (double)ITERS * 128, d_out, d_res);
-        if (b <= 512) {
-            run("ffma2_ldcu_lds<4, lds/16taps>", [&] { k_ffma2_ldcu_lds<4, 16><<<grid, b, 65536>>>(d_out, d_res, 0.5f); }, grid, b, (double)ITERS * 128, d_out, d_res);
-            run("ffma2_ldcu_lds<4, lds/4taps>", [&] { k_ffma2_ldcu_lds<4, 4><<<grid, b, 65536>>>(d_out, d_res, 0.5f); }, grid, b, (double)ITERS * 128, d_out, d_res);
-            run("ffma2_ldcu_lds<4, lds/1tap>", [&] { k_ffma2_ldcu_lds<4, 1><<<grid, b, 65536>>>(d_out, d_res, 0.5f); }, grid, b, (double)ITERS * 128, d_out, d_res);
+        if (b <= 512) {  // 17*b+16 float4 of shared memory
+            run("ffma2_ldcu_lds<4, lds/16taps>", [&] { k_ffma2_ldcu_lds<4, 16><<<grid, b, (17 * b + 16) * 16>>>(d_out, d_res, 0.5f); }, grid, b, (double)ITERS * 128, d_out, d_res);
+            run("ffma2_ldcu_lds<4, lds/4taps>", [&] { k_ffma2_ldcu_lds<4, 4><<<grid, b, (17 * b + 16) * 16>>>(d_out, d_res, 0.5f); }, grid, b, (double)ITERS * 128, d_out, d_res);
+            run("ffma2_ldcu_lds<4, lds/1tap>", [&] { k_ffma2_ldcu_lds<4, 1><<<grid, b, (17 * b + 16) * 16>>>(d_out, d_res, 0.5f); }, grid, b, (double)ITERS * 128, d_out, d_res);
         }
     }
     return 0;
