@@ -30,6 +30,8 @@ struct RunParams {
     int halo_rows;               // extra rows staged behind each tile
     int n_streams;
     int vec_store;               // 1 if out pointer / stride allow 16-byte stores
+    int l2_ahead;                // kernel P: chunks of L2 prefetch distance (0 = off)
+    int stagger_cycles;          // start delay of every other compute warp (see ddc_fused_kernel)
     int debug_mode;              // 0 normal; 1 compute only (no TMA, no waits); 2 memory only (no FIR) -- ceilings for tuning
 };
 

@@ -154,7 +154,7 @@ ddc_fused_kernel(const __grid_constant__ RunParams p, const __grid_constant__ Ta
         // ------------------------------------------------ producer warp
         const int n_sr = NROWS / S + (p.halo_rows + S - 1) / S;  // super-rows per stage
         const long long want = (long long)(NROWS + p.halo_rows) * ROW;
-        for (int it = 0; it < n_iter && p.debug_mode != 1; ++it) {
+        for (int it = 0; it < n_iter && p.debug_mode != 1 && p.debug_mode != 3; ++it) {
             const int stage = it % STAGES;
             const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
             mbar_wait(&empty_bar[stage], ph ^ 1u);
@@ -225,10 +225,18 @@ ddc_fused_kernel(const __grid_constant__ RunParams p, const __grid_constant__ Ta
             rot_thr[r] = nco_rot((unsigned long long)((long long)(g * R + rbeg + r) * D) * p.step_fx);
         const unsigned long long tile_dph = (unsigned long long)((long long)TILE_OUT * D) * p.step_fx;
 
+        // The two (KS = 1) or four (KS = 2) compute warps that share an SM sub-partition do identical work and would reach
+        // their epilogues together, leaving the FMA pipe idle; starting every other one half a tile late keeps one
+        // warp in its FMA loop while its neighbour rotates and stores.
+        if (p.stagger_cycles > 0 && ((warp >> 2) & 1)) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < p.stagger_cycles) {}
+        }
+
         for (int it = 0; it < n_iter; ++it) {
             const int stage = it % STAGES;
             const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-            if (p.debug_mode != 1) mbar_wait(&full_bar[stage], ph);
+            if (p.debug_mode != 1 && p.debug_mode != 3) mbar_wait(&full_bar[stage], ph);
             const float* sbuf = buf + (size_t)stage * stage_floats;
 
 #ifndef DDCB200_SPLIT_ACC
@@ -259,9 +267,11 @@ ddc_fused_kernel(const __grid_constant__ RunParams p, const __grid_constant__ Ta
                 for (int jj = 0; jj < R; ++jj) {
                     const int srel = jj + R - 1;  // newest block of this step, relative to block j0 (row p0)
                     const float* src = (srel / R) ? p1 : p0;
+                    if (p.debug_mode != 3) {  // 3: compute only AND no shared-memory loads in the loop (FMA ceiling)
 #pragma unroll
-                    for (int v = 0; v < V; ++v)
-                        xw[srel % R][v] = *reinterpret_cast<const float4*>(src + (srel % R) * D + 4 * v);
+                        for (int v = 0; v < V; ++v)
+                            xw[srel % R][v] = *reinterpret_cast<const float4*>(src + (srel % R) * D + 4 * v);
+                    }
                     const float4* tp = tbase + (size_t)(j0 + jj) * (D / 2);
 #pragma unroll
                     for (int v = 0; v < V; ++v) {
@@ -284,7 +294,7 @@ ddc_fused_kernel(const __grid_constant__ RunParams p, const __grid_constant__ Ta
                 acc[r] = (NA == 2) ? make_float2(accp[r][0].x + accp[r][NA - 1].x, accp[r][0].y + accp[r][NA - 1].y) : accp[r][0];
             // all shared-memory reads of this stage are done -> hand the slot back to the producer
             __syncwarp();
-            if (lane == 0 && p.debug_mode != 1) mbar_arrive(&empty_bar[stage]);
+            if (lane == 0 && p.debug_mode != 1 && p.debug_mode != 3) mbar_arrive(&empty_bar[stage]);
 
             // epilogue: combine tap halves, rotate each output by the NCO phase of its first input sample, store
             float2 y[RO];

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "ddc_kernels.cuh"
+#include "ddc_kernel_p.cuh"
 
 using namespace ddck;
 
@@ -77,6 +78,8 @@ struct ddcb200 {
     int64_t launches = 0;
     int force_variant = 0;
     int debug_mode = 0;
+    int stagger_cycles = 0;
+    int l2_ahead = 0;
     std::string last_variant = "none";
     bool smem_attr_set = false;
 };
@@ -130,6 +133,10 @@ int ensure_ring(ddcb200* h, int n_taps) {
     return DDCB200_OK;
 }
 
+static inline bool aligned_f32(const void* d_in, int64_t in_stride, bool packed) {
+    return !packed && (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (in_stride % 4 == 0);
+}
+
 template <int D, int R, int KS, int MAXT>
 int launch_fused(ddcb200* h, RunParams& p, const float2* ctaps_host, cudaStream_t st, int grid_limit) {
     using C = FusedCfg<D, R, kS, KS>;
@@ -166,6 +173,46 @@ int launch_fused_t(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, 
     return launch_fused<D, R, 1, kMaxTapsFused>(h, p, ct, st, grid_limit);
 }
 
+template <int D, int JT, int KS>
+int launch_p(ddcb200* h, RunParams& p, const float2* ctaps_host, cudaStream_t st) {
+    using C = PCfg<D, JT, KS>;
+    constexpr int MAXT = JT * D;
+    auto kern = ddc_fused_p_kernel<D, JT, KS, MAXT>;
+    const size_t smem = C::HDR_BYTES + (size_t)C::NSLOT * C::SLOT_FLOATS * sizeof(float);
+    static bool attr_set[64] = {};
+    if (h->device < 64 && !attr_set[h->device]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[h->device] = true;
+    }
+    TapsParam<MAXT> tp;
+    std::memset(&tp, 0, sizeof(tp));
+    std::memcpy(tp.c2, ctaps_host, sizeof(float2) * (size_t)std::min(p.n_taps, MAXT));
+    const long long grid = std::min<long long>(p.total_tiles, h->sm_count);
+    kern<<<(unsigned)grid, C::NWARPS * 32 + 32 * C::NPROD, smem, st>>>(p, tp);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    char name[96];
+    snprintf(name, sizeof(name), "fused_phase_major<D%d,R%d,J%d,KS%d,SLOTS%d>", D, C::R, JT, KS, C::NSLOT);
+    h->last_variant = name;
+    return DDCB200_OK;
+}
+
+template <int D>
+int launch_p_j(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, int jt, int ks) {
+    if (ks == 2) {
+        switch (jt) {
+            case 4: return launch_p<D, 4, 2>(h, p, ct, st);
+            case 8: return launch_p<D, 8, 2>(h, p, ct, st);
+            default: return launch_p<D, 16, 2>(h, p, ct, st);
+        }
+    }
+    switch (jt) {
+        case 4: return launch_p<D, 4, 1>(h, p, ct, st);
+        case 8: return launch_p<D, 8, 1>(h, p, ct, st);
+        default: return launch_p<D, 16, 1>(h, p, ct, st);
+    }
+}
+
 // Core dispatcher for device-resident data.
 int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int64_t n_streams, int64_t in_stride,
                double step, int64_t sample_offset, ddcb200_c64* d_out, int64_t out_stride, cudaStream_t st,
@@ -193,6 +240,8 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
     p.phase0_fx = phase_of(step, sample_offset);
     p.vec_store = ((reinterpret_cast<uintptr_t>(d_out) % 16) == 0 && (out_stride % 2) == 0) ? 1 : 0;
     p.debug_mode = h->debug_mode;
+    p.stagger_cycles = h->stagger_cycles;
+    p.l2_ahead = h->l2_ahead;
 
     // ---- fused path eligibility ---------------------------------------------------------------------------
     int R = 0;
@@ -207,7 +256,7 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
     long long tiles = 0;
     int n_taps_pad = T, J = 0, halo_rows = 0, ks = 1;
     const bool aligned = !packed && (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (in_stride % 4 == 0);
-    if (R > 0 && aligned && h->force_variant != 1) {
+    if (R > 0 && aligned && h->force_variant != 1 && h->force_variant != 5 && h->force_variant != 6) {
         J = (T + D - 1) / D;
         // tap split 2 (16 compute warps) whenever it costs no extra zero taps; option "variant" 2 / 3 force KS 1 / 2
         ks = (J % (2 * R) == 0 && R <= 4) ? 2 : 1;
@@ -219,6 +268,27 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         halo_rows = (J + R - 2) / R;
         const long long tile_out = 256LL * R;
         if (n_taps_pad <= kMaxTapsFused) tiles = (M + tile_out - 1) / tile_out;  // the last one may be ragged
+    }
+
+    // ---- kernel P (phase-major, R = 128/D outputs per thread): short polyphase branches, J = ceil(T/D) <= 16 ------
+    if (aligned_f32(d_in, in_stride, packed) && (D == 16 || D == 32 || D == 64) && (T + D - 1) / D <= 16 &&
+        (h->force_variant == 0 || h->force_variant == 5 || h->force_variant == 6)) {
+        const int ksp = (h->force_variant == 5) ? 1 : 2;   // option "variant": 5 = one warp per chunk, 6 (= auto) = two
+        const int Jp = (T + D - 1) / D;
+        const int jt = Jp <= 4 ? 4 : (Jp <= 8 ? 8 : 16);
+        std::vector<float2> ctp((size_t)jt * D);
+        make_ctaps(h, step, jt * D, ctp.data());
+        const long long chunk_out = 32LL * (128 / D);   // PCfg::CHUNK_OUT
+        p.tiles_per_stream = (M + chunk_out - 1) / chunk_out;
+        p.total_tiles = p.tiles_per_stream * n_streams;
+        p.n_taps = jt * D;
+        p.n_tap_blocks = jt;
+        p.m_begin = 0;
+        switch (D) {
+            case 16: return launch_p_j<16>(h, p, ctp.data(), st, jt, ksp);
+            case 32: return launch_p_j<32>(h, p, ctp.data(), st, jt, ksp);
+            default: return launch_p_j<64>(h, p, ctp.data(), st, jt, ksp);
+        }
     }
 
     std::vector<float2> ct((size_t)std::max(n_taps_pad, T));
@@ -553,6 +623,14 @@ int ddcb200_set_option(ddcb200_t* h, const char* key, int64_t value) {
     if (!h || !key) return fail(DDCB200_EINVAL, "set_option: bad arguments");
     if (!strcmp(key, "variant")) {
         h->force_variant = (int)value;
+        return DDCB200_OK;
+    }
+    if (!strcmp(key, "l2_ahead")) {
+        h->l2_ahead = (int)value;
+        return DDCB200_OK;
+    }
+    if (!strcmp(key, "stagger_cycles")) {
+        h->stagger_cycles = (int)value;
         return DDCB200_OK;
     }
     if (!strcmp(key, "debug_mode")) {
