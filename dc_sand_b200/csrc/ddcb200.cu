@@ -197,6 +197,39 @@ int launch_p(ddcb200* h, RunParams& p, const float2* ctaps_host, cudaStream_t st
     return DDCB200_OK;
 }
 
+template <int D, int JT>
+int launch_p10(ddcb200* h, RunParams& p, const float2* ctaps_host, cudaStream_t st) {
+    using C = P10Cfg<D, JT>;
+    constexpr int MAXT = JT * D;
+    auto kern = ddc_fused_p10_kernel<D, JT, MAXT>;
+    const size_t smem = 512 + (size_t)C::FLOAT_BYTES + (size_t)C::NRAW * C::RAW_BYTES;
+    static bool attr_set[64] = {};
+    if (h->device < 64 && !attr_set[h->device]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[h->device] = true;
+    }
+    TapsParam<MAXT> tp;
+    std::memset(&tp, 0, sizeof(tp));
+    std::memcpy(tp.c2, ctaps_host, sizeof(float2) * (size_t)std::min(p.n_taps, MAXT));
+    const long long grid = std::min<long long>(p.total_tiles, h->sm_count);
+    kern<<<(unsigned)grid, C::NWARPS * 32 + 32 * C::NPROD, smem, st>>>(p, tp);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    char name[96];
+    snprintf(name, sizeof(name), "fused_phase_major_packed10<D%d,R%d,J%d,RAWSLOTS%d>", D, C::R, JT, C::NRAW);
+    h->last_variant = name;
+    return DDCB200_OK;
+}
+
+template <int D>
+int launch_p10_j(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, int jt) {
+    switch (jt) {
+        case 4: return launch_p10<D, 4>(h, p, ct, st);
+        case 8: return launch_p10<D, 8>(h, p, ct, st);
+        default: return launch_p10<D, 16>(h, p, ct, st);
+    }
+}
+
 template <int D>
 int launch_p_j(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, int jt, int ks) {
     if (ks == 2) {
@@ -270,10 +303,30 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         if (n_taps_pad <= kMaxTapsFused) tiles = (M + tile_out - 1) / tile_out;  // the last one may be ragged
     }
 
+    // ---- packed 10-bit input: phase-major kernel with the unpack fused behind the TMA ring -------------------------
+    if (packed && (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (in_stride % 16 == 0) && (D == 16 || D == 32 || D == 64) &&
+        (T + D - 1) / D <= 16 && h->force_variant != 1) {
+        const int Jp = (T + D - 1) / D;
+        const int jt = Jp <= 4 ? 4 : (Jp <= 8 ? 8 : 16);
+        std::vector<float2> ctp((size_t)jt * D);
+        make_ctaps(h, step, jt * D, ctp.data());
+        const long long chunk_out = 32LL * (128 / D);
+        p.tiles_per_stream = (M + chunk_out - 1) / chunk_out;
+        p.total_tiles = p.tiles_per_stream * n_streams;
+        p.n_taps = jt * D;
+        p.n_tap_blocks = jt;
+        p.m_begin = 0;
+        switch (D) {
+            case 16: return launch_p10_j<16>(h, p, ctp.data(), st, jt);
+            case 32: return launch_p10_j<32>(h, p, ctp.data(), st, jt);
+            default: return launch_p10_j<64>(h, p, ctp.data(), st, jt);
+        }
+    }
+
     // ---- kernel P (phase-major, R = 128/D outputs per thread): short polyphase branches, J = ceil(T/D) <= 16 ------
     if (aligned_f32(d_in, in_stride, packed) && (D == 16 || D == 32 || D == 64) && (T + D - 1) / D <= 16 &&
         (h->force_variant == 0 || h->force_variant == 5 || h->force_variant == 6)) {
-        const int ksp = (h->force_variant == 5) ? 1 : 2;   // option "variant": 5 = one warp per chunk, 6 (= auto) = two
+        const int ksp = (h->force_variant == 6) ? 2 : 1;   // option "variant": 5 (= auto) one warp per chunk, 6 = two (slower)
         const int Jp = (T + D - 1) / D;
         const int jt = Jp <= 4 ? 4 : (Jp <= 8 ? 8 : 16);
         std::vector<float2> ctp((size_t)jt * D);
@@ -379,9 +432,9 @@ int run_host(ddcb200* h, const void* h_in, bool packed, int64_t n_samples, int64
     // byte boundary and float chunks stay 16-byte aligned
     int64_t per_stream = std::max<int64_t>(h->chunk_samples / n_streams, (int64_t)4 * T);
     int64_t m_chunk = std::max<int64_t>(per_stream / D, 1);
-    m_chunk = ((m_chunk + 3) / 4) * 4;
+    m_chunk = ((m_chunk + 63) / 64) * 64;   // chunk starts stay 16-byte aligned for float32 AND packed (64 samples = 80 B)
     const int64_t n_chunks = (M + m_chunk - 1) / m_chunk;
-    const int64_t in_chunk_samples = ((m_chunk - 1) * D + T + 3) / 4 * 4;
+    const int64_t in_chunk_samples = ((m_chunk - 1) * D + T + 63) / 64 * 64;
     const size_t in_elem_bytes_num = packed ? 5 : 16, in_elem_den = 4;  // bytes per 4 samples
     const size_t in_row_bytes = (size_t)in_chunk_samples / in_elem_den * in_elem_bytes_num;
     int rc = ensure_chunks(h, in_row_bytes * (size_t)n_streams + 64, (size_t)m_chunk * (size_t)n_streams);
