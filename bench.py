@@ -303,6 +303,23 @@ def run_ours(args):
     # parity spot check of what the timed calls produced (device-resident result vs host-path result)
     same = bool(torch.allclose(d_out[:, : min(m, 4096)].cpu(), h_out[:, : min(m, 4096)], rtol=0, atol=0))
 
+    # ---- optional final gather of the outputs over NCCL (outside the timed region; the hot path has no collective) ---
+    gather_ms = None
+    if world > 1:
+        from dc_sand_b200.scheduler import ShardedDDC
+
+        sh = ShardedDDC(world * n_streams, rank, world, ddc=ddc, center_freq=FC)
+        torch.cuda.synchronize()
+        dist.barrier()
+        g0 = time.perf_counter()
+        full = sh.gather(d_out, dst=0)
+        torch.cuda.synchronize()
+        gather_ms = (time.perf_counter() - g0) * 1e3
+        if rank == 0:
+            assert full.shape == (world * n_streams, m)
+            assert torch.equal(full[:n_streams], d_out)
+        del full
+
     # ---- max over ranks -------------------------------------------------------------------------------------------
     stats = torch.tensor([total_ms, e2e_s, float(np.median(kern_ms))], dtype=torch.float64, device=dev)
     if world > 1:
@@ -367,6 +384,7 @@ def run_ours(args):
                 "matches_device_path": same,
             },
             "gpu_launches": int(launches),
+            "final_gather_ms_untimed": gather_ms,
             "clocks": clk.summary(),
         }
         if args.gpus == 1 and not args.no_cpu:

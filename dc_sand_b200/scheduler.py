@@ -1,0 +1,143 @@
+"""Stream scheduler: shards independent antenna-polarisation streams across the GPUs of one box.
+
+Every stream of the reference operator is an independent 1-D problem (`DigitalDownConverter.run` is strictly 1-D,
+/root/reference/feng/ddc/src/ddc.py:121-188), so the partition is by stream, there is NO collective on the data path
+and no halo exchange.  Two ways to drive it:
+
+  * one process per GPU under torch.distributed (`ShardedDDC`): rank r owns streams shard_range(S, world, r); an
+    optional final gather of the [streams, M] complex64 outputs runs over NCCL (NVLink / NVSwitch) outside the hot path;
+  * one process, several devices (`MultiDeviceDDC`): one native handle per device driven from Python threads (ctypes
+    releases the GIL while the C ABI runs).
+
+Only the bookkeeping lives here; all arithmetic happens in libddcb200.so.
+"""
+from __future__ import annotations
+
+import threading
+from typing import Callable, Sequence
+
+import numpy as np
+
+
+def shard_range(n_streams: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Contiguous, balanced block of streams for `rank`: the first n % world ranks get one extra stream."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError(f"bad rank/world_size: {rank}/{world_size}")
+    if n_streams < 0:
+        raise ValueError("n_streams must be >= 0")
+    base, extra = divmod(n_streams, world_size)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_sizes(n_streams: int, world_size: int) -> list[int]:
+    return [b - a for a, b in (shard_range(n_streams, world_size, r) for r in range(world_size))]
+
+
+class ShardedDDC:
+    """One rank of a stream-sharded down-converter (one process per GPU, torch.distributed initialised by the caller).
+
+    `compute` maps a [s_local, N] tensor to a [s_local, M] complex64 tensor on the same device; by default it is
+    `DigitalDownConverter.run_tensor` of this rank's device.  It is injectable so that the sharding / gather logic can
+    be tested on CPU with the gloo backend (tests/test_scheduler.py) -- the product path always uses the CUDA operator.
+    """
+
+    def __init__(self, n_streams: int, rank: int, world_size: int, compute: Callable | None = None, ddc=None,
+                 center_freq: float | None = None):
+        self.n_streams = int(n_streams)
+        self.rank, self.world_size = int(rank), int(world_size)
+        self.start, self.stop = shard_range(self.n_streams, self.world_size, self.rank)
+        if compute is None:
+            if ddc is None or center_freq is None:
+                raise ValueError("pass either compute= or ddc= and center_freq=")
+            compute = lambda x: ddc.run_tensor(x, center_freq)  # noqa: E731
+        self._compute = compute
+
+    @property
+    def local_streams(self) -> range:
+        return range(self.start, self.stop)
+
+    def run_local(self, x_local):
+        """Down-convert this rank's streams. No communication."""
+        if x_local.shape[0] != self.stop - self.start:
+            raise ValueError(f"rank {self.rank} expects {self.stop - self.start} streams, got {x_local.shape[0]}")
+        return self._compute(x_local)
+
+    def gather(self, y_local, dst: int | None = None):
+        """Optional final gather of the outputs, stream order preserved.
+
+        dst=None -> every rank gets the full [streams, M] tensor (all_gather); dst=r -> only rank r (others get None).
+        Shards may differ by one stream; they are padded to the largest shard for the collective and trimmed after.
+        """
+        import torch
+        import torch.distributed as dist
+
+        sizes = shard_sizes(self.n_streams, self.world_size)
+        smax = max(sizes)
+        m = y_local.shape[1]
+        pad = y_local
+        if y_local.shape[0] < smax:
+            pad = torch.zeros((smax, m), dtype=y_local.dtype, device=y_local.device)
+            pad[: y_local.shape[0]] = y_local
+        # complex tensors travel as their float32 view (NCCL has no complex type)
+        flat = torch.view_as_real(pad.contiguous()).reshape(-1)
+        if dst is None:
+            out = torch.empty(self.world_size * flat.numel(), dtype=flat.dtype, device=flat.device)
+            dist.all_gather_into_tensor(out, flat)
+        else:
+            bufs = [torch.empty_like(flat) for _ in range(self.world_size)] if self.rank == dst else None
+            dist.gather(flat, bufs, dst=dst)
+            if self.rank != dst:
+                return None
+            out = torch.stack(bufs)
+        out = torch.view_as_complex(out.reshape(self.world_size, smax, m, 2))
+        return torch.cat([out[r, : sizes[r]] for r in range(self.world_size)], dim=0)
+
+
+class MultiDeviceDDC:
+    """Single-process driver: one DigitalDownConverter per device, streams sharded by `shard_range`, host arrays in/out."""
+
+    def __init__(self, decimation_factor: int, sampling_frequency: float, ddc_coeff_filename: str,
+                 devices: Sequence[int] | None = None):
+        from .ddc import DigitalDownConverter
+
+        if devices is None:
+            import torch
+
+            devices = list(range(torch.cuda.device_count()))
+        if not devices:
+            raise RuntimeError("MultiDeviceDDC needs at least one CUDA device (no CPU fallback)")
+        self.devices = list(devices)
+        self.workers = [DigitalDownConverter(decimation_factor, sampling_frequency, ddc_coeff_filename, device=d)
+                        for d in self.devices]
+
+    def run_batch(self, input_data: np.ndarray, center_freq: float) -> np.ndarray:
+        x = np.ascontiguousarray(input_data, dtype=np.float32)
+        if x.ndim != 2:
+            raise ValueError("run_batch needs a [streams, N] array")
+        s, n = x.shape
+        m = self.workers[0].out_len(n)
+        out = np.empty((s, m), dtype=np.complex64)
+        errs: list[BaseException] = []
+
+        def work(i):
+            a, b = shard_range(s, len(self.workers), i)
+            if a == b:
+                return
+            try:
+                self.workers[i].run_batch(x[a:b], center_freq, out=out[a:b])
+            except BaseException as e:  # propagate to the caller thread
+                errs.append(e)
+
+        threads = [threading.Thread(target=work, args=(i,)) for i in range(len(self.workers))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errs:
+            raise errs[0]
+        return out
+
+    def close(self):
+        for w in self.workers:
+            w.close()

@@ -1,0 +1,81 @@
+"""CPU tests of the stream scheduler (no CUDA): sharding arithmetic and the torch.distributed gather on the gloo
+backend with world_size 2 and 3 (unequal shards), with an injected stand-in for the per-rank compute."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from dc_sand_b200.scheduler import ShardedDDC, shard_range, shard_sizes
+
+
+def test_shard_range_partitions_every_stream_once():
+    for n in (0, 1, 7, 64, 128, 129):
+        for w in (1, 2, 3, 4, 8):
+            seen = []
+            for r in range(w):
+                a, b = shard_range(n, w, r)
+                assert 0 <= a <= b <= n
+                seen += list(range(a, b))
+            assert seen == list(range(n))
+            sizes = shard_sizes(n, w)
+            assert max(sizes) - min(sizes) <= 1 and sum(sizes) == n
+    assert shard_range(128, 8, 3) == (48, 64)
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+def _fake_ddc(x):
+    """Stand-in for the CUDA operator: [s, N] real -> [s, N // 4] complex64, a deterministic function of the input."""
+    y = x[:, ::4].to(torch.float32)
+    return torch.complex(y, -2.0 * y)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_streams, n, dst, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full = torch.arange(n_streams * n, dtype=torch.float32).reshape(n_streams, n)
+        sh = ShardedDDC(n_streams, rank, world, compute=_fake_ddc)
+        y_local = sh.run_local(full[sh.start : sh.stop])
+        got = sh.gather(y_local, dst=dst)
+        ref = _fake_ddc(full)
+        if dst is None or rank == dst:
+            ok = got is not None and got.shape == ref.shape and torch.equal(got, ref)
+        else:
+            ok = got is None
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_streams,dst", [(2, 8, None), (2, 5, 0), (3, 7, None)])
+def test_sharded_gather_over_gloo(world, n_streams, dst):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_streams, 64, dst, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = dict(q.get(timeout=10) for _ in range(world))
+    assert res == {r: True for r in range(world)}
+
+
+def test_run_local_checks_shard_size():
+    sh = ShardedDDC(8, 1, 2, compute=_fake_ddc)
+    assert list(sh.local_streams) == [4, 5, 6, 7]
+    with pytest.raises(ValueError):
+        sh.run_local(torch.zeros(3, 16))
