@@ -30,6 +30,7 @@ struct RunParams {
     int halo_rows;               // extra rows staged behind each tile
     int n_streams;
     int vec_store;               // 1 if out pointer / stride allow 16-byte stores
+    unsigned long long* dbg;     // optional diagnostic counters (wait cycles / total cycles of compute warps), or NULL
     int l2_ahead;                // kernel P: chunks of L2 prefetch distance (0 = off)
     int stagger_cycles;          // start delay of every other compute warp (see ddc_fused_kernel)
     int debug_mode;              // 0 normal; 1 compute only (no TMA, no waits); 2 memory only (no FIR) -- ceilings for tuning
@@ -125,6 +126,19 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// one elected lane of a converged warp (ptxas then predicates uniform-datapath instructions such as UBLKCP on it instead
+// of serialising "divergent" lanes in a BRA.U.ANY loop)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

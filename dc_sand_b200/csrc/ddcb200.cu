@@ -80,6 +80,7 @@ struct ddcb200 {
     int debug_mode = 0;
     int stagger_cycles = 0;
     int l2_ahead = 0;
+    unsigned long long* d_dbg = nullptr;   // diagnostic counters (option "dbg_counters")
     std::string last_variant = "none";
     bool smem_attr_set = false;
 };
@@ -230,6 +231,39 @@ int launch_p10_j(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, in
     }
 }
 
+template <int D, int JT>
+int launch_pd(ddcb200* h, RunParams& p, const float2* ctaps_host, cudaStream_t st) {
+    using C = PCfg<D, JT, 1>;
+    constexpr int MAXT = JT * D;
+    auto kern = ddc_fused_pd_kernel<D, JT, MAXT>;
+    const size_t smem = C::HDR_BYTES + (size_t)C::NSLOT * C::SLOT_FLOATS * sizeof(float);
+    static bool attr_set[64] = {};
+    if (h->device < 64 && !attr_set[h->device]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[h->device] = true;
+    }
+    TapsParam<MAXT> tp;
+    std::memset(&tp, 0, sizeof(tp));
+    std::memcpy(tp.c2, ctaps_host, sizeof(float2) * (size_t)std::min(p.n_taps, MAXT));
+    const long long grid = std::min<long long>(p.total_tiles, h->sm_count);
+    kern<<<(unsigned)grid, C::NWARPS * 32 + 32 * C::NPROD, smem, st>>>(p, tp);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    char name[96];
+    snprintf(name, sizeof(name), "fused_phase_major_deferred<D%d,R%d,J%d,SLOTS%d>", D, C::R, JT, C::NSLOT);
+    h->last_variant = name;
+    return DDCB200_OK;
+}
+
+template <int D>
+int launch_pd_j(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, int jt) {
+    switch (jt) {
+        case 4: return launch_pd<D, 4>(h, p, ct, st);
+        case 8: return launch_pd<D, 8>(h, p, ct, st);
+        default: return launch_pd<D, 16>(h, p, ct, st);
+    }
+}
+
 template <int D>
 int launch_p_j(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, int jt, int ks) {
     if (ks == 2) {
@@ -275,6 +309,7 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
     p.debug_mode = h->debug_mode;
     p.stagger_cycles = h->stagger_cycles;
     p.l2_ahead = h->l2_ahead;
+    p.dbg = h->d_dbg;
 
     // ---- fused path eligibility ---------------------------------------------------------------------------
     int R = 0;
@@ -337,6 +372,13 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         p.n_taps = jt * D;
         p.n_tap_blocks = jt;
         p.m_begin = 0;
+        if (h->force_variant == 0) {   // default: deferred-epilogue variant
+            switch (D) {
+                case 16: return launch_pd_j<16>(h, p, ctp.data(), st, jt);
+                case 32: return launch_pd_j<32>(h, p, ctp.data(), st, jt);
+                default: return launch_pd_j<64>(h, p, ctp.data(), st, jt);
+            }
+        }
         switch (D) {
             case 16: return launch_p_j<16>(h, p, ctp.data(), st, jt, ksp);
             case 32: return launch_p_j<32>(h, p, ctp.data(), st, jt, ksp);
@@ -554,6 +596,7 @@ void ddcb200_destroy(ddcb200_t* h) {
         if (h->ev_k[i]) cudaEventDestroy(h->ev_k[i]);
         if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
     }
+    if (h->d_dbg) cudaFree(h->d_dbg);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_in) cudaStreamDestroy(h->copy_in);
     if (h->copy_out) cudaStreamDestroy(h->copy_out);
@@ -676,6 +719,22 @@ int ddcb200_set_option(ddcb200_t* h, const char* key, int64_t value) {
     if (!h || !key) return fail(DDCB200_EINVAL, "set_option: bad arguments");
     if (!strcmp(key, "variant")) {
         h->force_variant = (int)value;
+        return DDCB200_OK;
+    }
+    if (!strcmp(key, "dbg_counters")) {   // 1: allocate + zero, 0: free, 2: print wait/total cycle ratio to stderr
+        DeviceGuard g(h->device);
+        if (value == 1) {
+            if (!h->d_dbg) CUDA_TRY(cudaMalloc(&h->d_dbg, 64));
+            CUDA_TRY(cudaMemset(h->d_dbg, 0, 64));
+        } else if (value == 2 && h->d_dbg) {
+            unsigned long long v[2] = {0, 0};
+            CUDA_TRY(cudaDeviceSynchronize());
+            CUDA_TRY(cudaMemcpy(v, h->d_dbg, 16, cudaMemcpyDeviceToHost));
+            fprintf(stderr, "dbg_counters: compute warps waited %llu of %llu cycles = %.2f %%\n", v[0], v[1], v[1] ? 100.0 * v[0] / v[1] : 0.0);
+        } else if (value == 0 && h->d_dbg) {
+            cudaFree(h->d_dbg);
+            h->d_dbg = nullptr;
+        }
         return DDCB200_OK;
     }
     if (!strcmp(key, "l2_ahead")) {
