@@ -74,6 +74,38 @@ __global__ void unpack10_kernel(const uint8_t* __restrict__ in, long long n_grou
     }
 }
 
+// Stage kernels: the reference exposes its three stages as separate methods (ddc.py:51-66, 85-100, 102-119).  The fused
+// kernels above are what run() uses; these exist so that the stage methods of the drop-in class also execute on the GPU.
+__global__ void mix_kernel(const float* __restrict__ x, const float2* __restrict__ cw, float2* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float xv = x[i];
+        const float2 c = cw[i];
+        out[i] = make_float2(xv * c.x, xv * c.y);   // float32 * complex64 -> complex64 (ddc.py:66)
+    }
+}
+
+// full-rate "valid" FIR of a complex64 sequence with real taps: y[n] = sum_k h[k] z[n + k], h = reversed taps / sum
+__global__ void fir_c64_kernel(const float2* __restrict__ z, const float* __restrict__ h, int n_taps, float2* __restrict__ out,
+                               long long n_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    float re = 0.f, im = 0.f;
+    for (int k = 0; k < n_taps; ++k) {
+        const float2 v = __ldg(z + i + k);
+        const float hk = __ldg(h + k);
+        re = fmaf(v.x, hk, re);
+        im = fmaf(v.y, hk, im);
+    }
+    out[i] = make_float2(re, im);
+}
+
+__global__ void decimate_c64_kernel(const float2* __restrict__ z, long long offset, int decim, float2* __restrict__ out,
+                                    long long n_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_out) out[i] = z[offset + i * decim];
+}
+
 // =============================================================================================================
 // Fused persistent kernel
 // =============================================================================================================

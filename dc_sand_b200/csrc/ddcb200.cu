@@ -663,6 +663,55 @@ int ddcb200_run_short_f32(ddcb200_t* h, const float* d_in, int64_t n_samples, do
     return DDCB200_OK;
 }
 
+int ddcb200_mix_f32(ddcb200_t* h, const float* d_x, const ddcb200_c64* d_cw, ddcb200_c64* d_out, int64_t n, void* cuda_stream) {
+    if (!h || !d_x || !d_cw || !d_out || n <= 0) return fail(DDCB200_EINVAL, "mix: bad arguments");
+    DeviceGuard g(h->device);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    mix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_x, reinterpret_cast<const float2*>(d_cw),
+                                                            reinterpret_cast<float2*>(d_out), n);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return DDCB200_OK;
+}
+
+int ddcb200_fir_c64(ddcb200_t* h, const ddcb200_c64* d_in, int64_t n_in, ddcb200_c64* d_out, void* cuda_stream) {
+    if (!h || !d_in || !d_out) return fail(DDCB200_EINVAL, "fir: bad arguments");
+    const int T = (int)h->taps.size();
+    if (n_in < T) return fail(DDCB200_ETOOSHORT, "fir: n_in (%lld) < n_taps (%d)", (long long)n_in, T);
+    DeviceGuard g(h->device);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    int rc = ensure_ring(h, T);
+    if (rc) return rc;
+    const int slot = h->ring_pos;
+    h->ring_pos = (h->ring_pos + 1) % ddcb200::kRing;
+    CUDA_TRY(cudaEventSynchronize(h->ring_ev[slot]));
+    float* hh = reinterpret_cast<float*>(h->h_ctaps[slot]);
+    for (int k = 0; k < T; ++k) hh[k] = (float)(h->taps[T - 1 - k] / h->taps_sum);
+    CUDA_TRY(cudaMemcpyAsync(h->d_ctaps[slot], hh, sizeof(float) * T, cudaMemcpyHostToDevice, st));
+    const long long n_out = n_in - T + 1;
+    fir_c64_kernel<<<(unsigned)((n_out + 127) / 128), 128, 0, st>>>(reinterpret_cast<const float2*>(d_in),
+                                                                    reinterpret_cast<const float*>(h->d_ctaps[slot]), T,
+                                                                    reinterpret_cast<float2*>(d_out), n_out);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(h->ring_ev[slot], st));
+    h->launches++;
+    return DDCB200_OK;
+}
+
+int ddcb200_decimate_c64(ddcb200_t* h, const ddcb200_c64* d_in, int64_t n_in, int64_t offset, ddcb200_c64* d_out,
+                         void* cuda_stream) {
+    if (!h || !d_in || !d_out || offset < 0) return fail(DDCB200_EINVAL, "decimate: bad arguments");
+    if (n_in <= offset) return DDCB200_OK;
+    DeviceGuard g(h->device);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    const long long n_out = (n_in - offset + h->decim - 1) / h->decim;
+    decimate_c64_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(d_in), offset, h->decim,
+                                                                         reinterpret_cast<float2*>(d_out), n_out);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return DDCB200_OK;
+}
+
 int ddcb200_run_host_f32(ddcb200_t* h, const float* h_in, int64_t n_samples, int64_t n_streams, int64_t in_stride,
                          double step, int64_t sample_offset, ddcb200_c64* h_out, int64_t out_stride) {
     if (!h) return fail(DDCB200_EINVAL, "null handle");

@@ -165,6 +165,55 @@ class DigitalDownConverter:
         )
         return out
 
+    # ---- the reference's stage methods (run() itself is fused; these keep the stage API on the GPU) ----------------
+    def _stage_call(self, fn_name, arrays, n_out, *args):
+        """Copy host arrays to the device, run one stage entry point of the C ABI, return the complex64 result."""
+        import torch
+
+        dev = torch.device("cuda", self.device)
+        d = [torch.from_numpy(a).to(dev) for a in arrays]
+        out = torch.empty(max(n_out, 1), dtype=torch.complex64, device=dev)
+        fn = getattr(_lib.load(), fn_name)
+        ptrs = [t.data_ptr() for t in d]
+        _lib.check(fn(self._get_handle(), *ptrs, *args(out), _torch_stream(torch, dev)), fn_name)
+        return out[:n_out].cpu().numpy()
+
+    def _mix(self, mixing_carrier_wave: np.ndarray, input_data: np.ndarray) -> np.ndarray:
+        """Multiply mixing CW with input data (ddc.py:50-66): float32[N] x complex64[N] -> complex64[N]."""
+        cw = np.ascontiguousarray(mixing_carrier_wave, dtype=np.complex64)
+        x = np.ascontiguousarray(input_data, dtype=np.float32)
+        if x.ndim != 1 or cw.shape != x.shape:
+            raise ValueError(f"operands could not be broadcast together with shapes {x.shape} {cw.shape}")
+        if x.size == 0:
+            return np.empty(0, dtype=np.complex64)
+        return self._stage_call("ddcb200_mix_f32", [x, cw], x.size, lambda out: (out.data_ptr(), x.size))
+
+    def _bandpass_fir_filter(self, input_data: np.ndarray) -> np.ndarray:
+        """Full-rate "valid" FIR divided by sum(taps) (ddc.py:85-100): complex64[N] -> complex128[N - T + 1].
+
+        The device computes in float32 (complex64); the result is widened to the reference's complex128."""
+        z = np.ascontiguousarray(input_data, dtype=np.complex64)
+        n_taps = len(self.ddc_filter_coeffs)
+        if z.ndim != 1 or z.size < n_taps:
+            raise ValueError(f"Too few samples in input data. Received {z.size} < {n_taps} taps")
+        n_out = z.size - n_taps + 1
+        y = self._stage_call("ddcb200_fir_c64", [z], n_out, lambda out: (z.size, out.data_ptr()))
+        return y.astype(np.complex128)
+
+    def _decimate(self, input_data: np.ndarray, decimate_offset: int = 0) -> np.ndarray:
+        """Keep every decimation_factor-th sample starting at decimate_offset (ddc.py:102-119)."""
+        src = np.asarray(input_data)
+        z = np.ascontiguousarray(src, dtype=np.complex64)
+        off = int(decimate_offset)
+        if z.ndim != 1 or off < 0:
+            raise ValueError("input_data must be 1-D and decimate_offset >= 0")
+        d = int(self.decimation_factor)
+        n_out = max(0, -(-(z.size - off) // d))
+        if n_out == 0:
+            return np.empty(0, dtype=src.dtype if np.iscomplexobj(src) else np.complex64)
+        y = self._stage_call("ddcb200_decimate_c64", [z], n_out, lambda out: (z.size, off, out.data_ptr()))
+        return y.astype(np.complex128) if src.dtype == np.complex128 else y
+
     # ---- packed 10-bit input (reference stub: ddc.py:68-83) ---------------------------------------------------
     def _decode_8bit_to_10bit_to_float_data(self, data_8bit: np.ndarray) -> np.ndarray:
         """Convert 8-bit-packed 10-bit digitiser samples to float32 on the GPU (the reference only has `pass`).

@@ -95,6 +95,16 @@ int ddcb200_unpack10(ddcb200_t* handle, const uint8_t* d_in, int64_t n_samples, 
 int ddcb200_run_short_f32(ddcb200_t* handle, const float* d_in, int64_t n_samples, double phase_step_cycles,
                           int64_t sample_offset, ddcb200_c64* d_out, void* cuda_stream);
 
+/* ---- stage entry points (device pointers) ------------------------------------------------------------------------
+ * The reference exposes its stages as methods; run() here is fused, these let the drop-in class keep the stage methods
+ * on the GPU: _mix (ddc.py:51-66), _bandpass_fir_filter (ddc.py:85-100: full-rate "valid" FIR / sum(taps), complex64
+ * in, n_in - n_taps + 1 complex64 out), _decimate (ddc.py:102-119: z[offset::D], ceil((n_in - offset) / D) out). */
+int ddcb200_mix_f32(ddcb200_t* handle, const float* d_x, const ddcb200_c64* d_cw, ddcb200_c64* d_out, int64_t n,
+                    void* cuda_stream);
+int ddcb200_fir_c64(ddcb200_t* handle, const ddcb200_c64* d_in, int64_t n_in, ddcb200_c64* d_out, void* cuda_stream);
+int ddcb200_decimate_c64(ddcb200_t* handle, const ddcb200_c64* d_in, int64_t n_in, int64_t offset, ddcb200_c64* d_out,
+                         void* cuda_stream);
+
 /* ---- host-buffer entry points (what DigitalDownConverter.run binds to) -------------------------------------
  * Replace DigitalDownConverter.run (ddc.py:121-188) for host arrays: time-chunked, double-buffered
  * H2D -> fused kernel -> D2H on two CUDA streams, synchronous on return.  Pinned host memory (see

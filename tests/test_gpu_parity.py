@@ -207,3 +207,28 @@ def test_large_stream_windows_against_oracle(taps_dir):
     y2 = ddc.run_tensor(xt * 2.0, 100e6)
     torch.cuda.synchronize()
     assert torch.equal(y2, yt * 2.0)
+
+
+def test_stage_methods_match_reference_stages(taps_dir):
+    """_mix / _bandpass_fir_filter / _decimate (ddc.py:50-66, 85-119) run on the GPU and, chained, reproduce run()."""
+    from scipy import signal
+
+    n = 40_000
+    x = synth.digitiser_stream(n, 77).astype(np.float32)
+    ddc = _ddc(taps_dir, 16)
+    cw = orc.nco(n, 100e6, FS)
+    mixed = ddc._mix(mixing_carrier_wave=cw, input_data=x)
+    assert mixed.dtype == np.complex64
+    assert np.array_equal(mixed, x * cw)                       # one float32 multiply per component: bit-exact
+    filt = ddc._bandpass_fir_filter(mixed)
+    ref = signal.convolve(mixed, ddc.ddc_filter_coeffs, mode="valid") / sum(ddc.ddc_filter_coeffs)
+    assert filt.dtype == np.complex128 and filt.shape == ref.shape
+    emax, el2 = rel_err(filt, ref)
+    assert emax <= TOL_MAX and el2 <= TOL_L2, (emax, el2)
+    for off in (0, 3, 15):
+        dec = ddc._decimate(ref, off)
+        assert dec.dtype == np.complex128
+        assert np.array_equal(dec.astype(np.complex64), ref[off::16].astype(np.complex64))
+    assert len(ddc._decimate(ref[:5], 7)) == 0
+    emax, el2 = rel_err(ddc._decimate(filt), ddc.run(x, 100e6))
+    assert emax <= TOL_MAX and el2 <= TOL_L2, (emax, el2)
