@@ -45,6 +45,20 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(workload: str, variant: str):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the committed
+    `ncu --set full` capture of this workload (profiles/ncu_traffic.json); None if the capture is of another kernel."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(p) as f:
+            rec = json.load(f).get(workload)
+    except (OSError, ValueError):
+        return None
+    if not rec or not variant.startswith(rec.get("variant_prefix", "\0")):
+        return None
+    return rec.get("dram_bytes_per_launch")
+
+
 class ClockSampler:
     """Samples SM clock / throttle reasons with NVML while the timed region runs."""
 
@@ -252,16 +266,18 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
 
-    def device_pass(steps, timed):
+    def device_pass(steps, per_launch_events):
         evs = []
         with torch.cuda.stream(stream):
             for _ in range(steps):
-                e0 = torch.cuda.Event(enable_timing=True)
-                e1 = torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
+                if per_launch_events:
+                    e0 = torch.cuda.Event(enable_timing=True)
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
                 ddc.run_tensor(d_in, FC, out=d_out, packed=packed)
-                e1.record(stream)
-                evs.append((e0, e1))
+                if per_launch_events:
+                    e1.record(stream)
+                    evs.append((e0, e1))
         return evs
 
     # warm-up
@@ -269,18 +285,25 @@ def run_ours(args):
     torch.cuda.synchronize()
     barrier()
     launches0 = ddc.launch_count
+    # Timed region: K steps queued back to back on one stream between two CUDA events (an event pair around every launch
+    # would put two timestamp packets between consecutive kernels and measure those as well).
     with ClockSampler(local) as clk:
         torch.cuda.synchronize()
         t_start = torch.cuda.Event(enable_timing=True)
         t_end = torch.cuda.Event(enable_timing=True)
-        t_start.record(stream)
-        evs = device_pass(args.steps, True)
-        t_end.record(stream)
+        with torch.cuda.stream(stream):
+            t_start.record(stream)
+        device_pass(args.steps, False)
+        with torch.cuda.stream(stream):
+            t_end.record(stream)
         torch.cuda.synchronize()
     launches = ddc.launch_count - launches0
     total_ms = t_start.elapsed_time(t_end)
-    kern_ms = [a.elapsed_time(b) for a, b in evs]
     barrier()
+    # diagnostic, outside the timed region: the same launches with an event pair around each one
+    evs = device_pass(min(args.steps, 20), True)
+    torch.cuda.synchronize()
+    kern_ms = [a.elapsed_time(b) for a, b in evs]
     variant = ddc.last_variant
 
     # ---- e2e: host buffers through the C ABI (H2D + kernel + D2H per step) ---------------------------------------
@@ -301,7 +324,9 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     # parity spot check of what the timed calls produced (device-resident result vs host-path result)
-    same = bool(torch.allclose(d_out[:, : min(m, 4096)].cpu(), h_out[:, : min(m, 4096)], rtol=0, atol=0))
+    # (tolerance, not bit equality: the host path runs time chunks, which may pair outputs differently in the fast FIR)
+    a_dev, a_host = d_out[:, : min(m, 4096)].cpu(), h_out[:, : min(m, 4096)]
+    same = bool((a_dev - a_host).abs().max() <= 1e-5 * a_dev.abs().max())
 
     # ---- optional final gather of the outputs over NCCL (outside the timed region; the hot path has no collective) ---
     gather_ms = None
@@ -333,7 +358,8 @@ def run_ours(args):
         b_in = 1.25 if packed else 4.0
         alg_bytes = n_streams * n * (b_in + 8.0 / D)            # per launch, per GPU
         flops = 4.0 * T * m * n_streams                         # 2T real FMAs per output
-        kern_s = float(np.mean(kern_ms)) * 1e-3
+        # average launch duration over the timed region (the region holds nothing but these launches, back to back)
+        kern_s = total_ms * 1e-3 / max(int(launches), 1)
         achieved = alg_bytes / kern_s / 1e9
         line = {
             "metric": "ddc_input_gsamples_per_s",
@@ -364,13 +390,13 @@ def run_ours(args):
                 "peak": hbm_peak,
                 "unit": "GB/s",
                 "frac": achieved / hbm_peak,
-                "traffic": None,
+                "traffic": ncu_traffic(args.workload if (args.gpus == 1 or args.workload != "c2") else "c5", variant),
                 "peak_source": peak_src,
                 "frac_of_nominal_8TBs": achieved / 8000.0,
                 "fp32_tflops": flops / kern_s / 1e12,
                 "fp32_frac_of_74.4": flops / kern_s / 1e12 / FP32_PEAK_TFLOPS,
-                "kernel_ms_mean": float(np.mean(kern_ms)),
-                "kernel_ms_median": kern_med_ms,
+                "kernel_ms_mean": kern_s * 1e3,
+                "kernel_ms_isolated_median": kern_med_ms,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "flop_per_launch": flops,
             },

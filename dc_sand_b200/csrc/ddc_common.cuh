@@ -56,6 +56,49 @@ __device__ __forceinline__ float2 nco_rot(unsigned long long ph) {
     return o;
 }
 
+// Branch-free variant for code that must stay one basic block (deferred epilogues): after the integer quadrant reduction
+// |x| <= 1/4, so sin(pi x) = x P(x^2) and cos(pi x) = Q(x^2) with degree-3 / degree-4 minimax polynomials (absolute error
+// 8.5e-8 / 5.8e-8, i.e. float32 rounding level); the quadrant is applied with selects.  sincospif carries branches for
+// special values that split the block.
+__device__ __forceinline__ float2 nco_rot_bf(unsigned long long ph) {
+    const uint32_t up = (uint32_t)(ph >> 32);
+    const uint32_t q = (up + 0x20000000u) >> 30;
+    const int32_t r = (int32_t)(up - (q << 30));
+    const float x = (float)r * (1.0f / 2147483648.0f);
+    const float s2 = x * x;
+    float sp = fmaf(s2, -5.890768766e-01f, 2.549767017e+00f);
+    sp = fmaf(sp, s2, -5.167707920e+00f);
+    sp = fmaf(sp, s2, 3.141592741e+00f);
+    float cs = fmaf(s2, 2.313292474e-01f, -1.335044503e+00f);
+    cs = fmaf(cs, s2, 4.058707237e+00f);
+    cs = fmaf(cs, s2, -4.934802055e+00f);
+    cs = fmaf(cs, s2, 1.0f);
+    const float re = cs, im = -(sp * x);                     // exp(-j pi x)
+    const bool sw = (q & 1u) != 0, ng = (q & 2u) != 0;       // times (-j)^q
+    const float a = sw ? im : re, b = sw ? -re : im;
+    return make_float2(ng ? -a : a, ng ? -b : b);
+}
+
+// predicated streaming stores (never a branch)
+__device__ __forceinline__ void st_cs_v4_if(float2* ptr, float a, float b, float c, float d, bool pr) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.u32 p, %5, 0;\n"
+        "@p st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};\n"
+        "}\n" ::"l"(ptr),
+        "f"(a), "f"(b), "f"(c), "f"(d), "r"((uint32_t)pr));
+}
+__device__ __forceinline__ void st_cs_v2_if(float2* ptr, float a, float b, bool pr) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.u32 p, %3, 0;\n"
+        "@p st.global.cs.v2.f32 [%0], {%1, %2};\n"
+        "}\n" ::"l"(ptr),
+        "f"(a), "f"(b), "r"((uint32_t)pr));
+}
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
@@ -95,6 +138,16 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_if(uint64_t* bar, bool pr) {   // predicated, never a branch
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.u32 p, %1, 0;\n"
+        "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"((uint32_t)pr)
+        : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(

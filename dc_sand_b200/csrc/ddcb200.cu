@@ -15,6 +15,7 @@
 
 #include "ddc_kernels.cuh"
 #include "ddc_kernel_p.cuh"
+#include "ddc_kernel_w.cuh"
 
 using namespace ddck;
 
@@ -102,6 +103,32 @@ void make_ctaps(const ddcb200* h, double step, int n_pad, float2* out) {
             out[k] = make_float2(0.f, 0.f);
         }
     }
+}
+
+// Kernel W (fast FIR, ddc_kernel_w.cuh): for tap pair i and phase d the three tap sets
+//   seq 0: c[2i D + d],  seq 1: c[2i D + d] + c[(2i+1) D + d],  seq 2: c[(2i+1) D + d]      at index (3i + seq) D + d,
+// formed in float64 from the folded taps and rounded to float32 once.
+void make_wtaps(const ddcb200* h, double step, int jt, int D, float2* out) {
+    const int T = (int)h->taps.size();
+    const double fstep = step - std::floor(step);
+    auto c = [&](int k, double& re, double& im) {
+        if (k >= T) { re = im = 0.0; return; }
+        const double hk = h->taps[T - 1 - k] / h->taps_sum;
+        double ph = fstep * (double)k;
+        ph -= std::floor(ph);
+        const double a = -2.0 * M_PI * ph;
+        re = hk * std::cos(a);
+        im = hk * std::sin(a);
+    };
+    for (int i = 0; i < jt / 2; ++i)
+        for (int d = 0; d < D; ++d) {
+            double er, ei, orr, oi;
+            c(2 * i * D + d, er, ei);
+            c((2 * i + 1) * D + d, orr, oi);
+            out[(3 * i + 0) * D + d] = make_float2((float)er, (float)ei);
+            out[(3 * i + 1) * D + d] = make_float2((float)(er + orr), (float)(ei + oi));
+            out[(3 * i + 2) * D + d] = make_float2((float)orr, (float)oi);
+        }
 }
 
 unsigned long long to_fx64(double frac01) {
@@ -264,6 +291,68 @@ int launch_pd_j(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, int
     }
 }
 
+template <int D, int JT>
+int launch_w(ddcb200* h, RunParams& p, cudaStream_t st, double step) {
+    using C = WCfg<D, JT>;
+    auto kern = ddc_fused_w_kernel<D, JT>;
+    const size_t smem = C::HDR_BYTES + (size_t)C::NSLOT * C::SLOT_FLOATS * sizeof(float);
+    static bool attr_set[64] = {};
+    if (h->device < 64 && !attr_set[h->device]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[h->device] = true;
+    }
+    TapsParam<C::NTW> tp;
+    make_wtaps(h, step, JT, D, reinterpret_cast<float2*>(tp.c2));
+    const long long grid = std::min<long long>(p.total_tiles, h->sm_count);
+    kern<<<(unsigned)grid, C::NWARPS * 32 + 32 * C::NPROD, smem, st>>>(p, tp);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    char name[96];
+    snprintf(name, sizeof(name), "fused_fast_fir<D%d,R%d,J%d,SLOTS%d>", D, C::R, JT, C::NSLOT);
+    h->last_variant = name;
+    return DDCB200_OK;
+}
+
+template <int D>
+int launch_w_j(ddcb200* h, RunParams& p, cudaStream_t st, double step, int jt) {
+    switch (jt) {
+        case 4: return launch_w<D, 4>(h, p, st, step);
+        case 8: return launch_w<D, 8>(h, p, st, step);
+        default: return launch_w<D, 16>(h, p, st, step);
+    }
+}
+
+template <int D, int JT>
+int launch_w10(ddcb200* h, RunParams& p, cudaStream_t st, double step) {
+    using C = W10Cfg<D, JT>;
+    auto kern = ddc_fused_w10_kernel<D, JT>;
+    const size_t smem = 512 + (size_t)C::FLOAT_BYTES + (size_t)C::NRAW * C::RAW_BYTES;
+    static bool attr_set[64] = {};
+    if (h->device < 64 && !attr_set[h->device]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[h->device] = true;
+    }
+    TapsParam<C::NTW> tp;
+    make_wtaps(h, step, JT, D, reinterpret_cast<float2*>(tp.c2));
+    const long long grid = std::min<long long>(p.total_tiles, h->sm_count);
+    kern<<<(unsigned)grid, C::NWARPS * 32 + 32 * C::NPROD, smem, st>>>(p, tp);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    char name[96];
+    snprintf(name, sizeof(name), "fused_fast_fir_packed10<D%d,R%d,J%d,RAWSLOTS%d>", D, C::R, JT, C::NRAW);
+    h->last_variant = name;
+    return DDCB200_OK;
+}
+
+template <int D>
+int launch_w10_j(ddcb200* h, RunParams& p, cudaStream_t st, double step, int jt) {
+    switch (jt) {
+        case 4: return launch_w10<D, 4>(h, p, st, step);
+        case 8: return launch_w10<D, 8>(h, p, st, step);
+        default: return launch_w10<D, 16>(h, p, st, step);
+    }
+}
+
 template <int D>
 int launch_p_j(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, int jt, int ks) {
     if (ks == 2) {
@@ -351,6 +440,14 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         p.n_taps = jt * D;
         p.n_tap_blocks = jt;
         p.m_begin = 0;
+        // fast-FIR variant where a thread has R = 8 outputs (D = 16); option "variant" 7 forces it, 5 forces the direct form
+        if ((D == 16 && h->force_variant != 5) || h->force_variant == 7) {
+            switch (D) {
+                case 16: return launch_w10_j<16>(h, p, st, step, jt);
+                case 32: return launch_w10_j<32>(h, p, st, step, jt);
+                default: return launch_w10_j<64>(h, p, st, step, jt);
+            }
+        }
         switch (D) {
             case 16: return launch_p10_j<16>(h, p, ctp.data(), st, jt);
             case 32: return launch_p10_j<32>(h, p, ctp.data(), st, jt);
@@ -360,7 +457,7 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
 
     // ---- kernel P (phase-major, R = 128/D outputs per thread): short polyphase branches, J = ceil(T/D) <= 16 ------
     if (aligned_f32(d_in, in_stride, packed) && (D == 16 || D == 32 || D == 64) && (T + D - 1) / D <= 16 &&
-        (h->force_variant == 0 || h->force_variant == 5 || h->force_variant == 6)) {
+        (h->force_variant == 0 || (h->force_variant >= 5 && h->force_variant <= 8))) {
         const int ksp = (h->force_variant == 6) ? 2 : 1;   // option "variant": 5 (= auto) one warp per chunk, 6 = two (slower)
         const int Jp = (T + D - 1) / D;
         const int jt = Jp <= 4 ? 4 : (Jp <= 8 ? 8 : 16);
@@ -372,7 +469,17 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         p.n_taps = jt * D;
         p.n_tap_blocks = jt;
         p.m_begin = 0;
-        if (h->force_variant == 0) {   // default: deferred-epilogue variant
+        // option "variant": 0 auto; 5 / 6 kernel P with one / two warps per chunk; 7 fast FIR (kernel W); 8 deferred-epilogue P.
+        // Auto picks the fast-FIR kernel where a thread has R = 8 outputs (D = 16) and the output rows allow 16-byte stores.
+        const bool want_w = h->force_variant == 7 || (h->force_variant == 0 && D == 16);
+        if (want_w) {   // any complex64-aligned output: the epilogue picks its 16-byte pairing per thread
+            switch (D) {
+                case 16: return launch_w_j<16>(h, p, st, step, jt);
+                case 32: return launch_w_j<32>(h, p, st, step, jt);
+                default: return launch_w_j<64>(h, p, st, step, jt);
+            }
+        }
+        if (h->force_variant == 0 || h->force_variant == 8) {   // deferred-epilogue variant
             switch (D) {
                 case 16: return launch_pd_j<16>(h, p, ctp.data(), st, jt);
                 case 32: return launch_pd_j<32>(h, p, ctp.data(), st, jt);

@@ -166,7 +166,7 @@ class DigitalDownConverter:
         return out
 
     # ---- the reference's stage methods (run() itself is fused; these keep the stage API on the GPU) ----------------
-    def _stage_call(self, fn_name, arrays, n_out, *args):
+    def _stage_call(self, fn_name, arrays, n_out, make_args):
         """Copy host arrays to the device, run one stage entry point of the C ABI, return the complex64 result."""
         import torch
 
@@ -175,7 +175,7 @@ class DigitalDownConverter:
         out = torch.empty(max(n_out, 1), dtype=torch.complex64, device=dev)
         fn = getattr(_lib.load(), fn_name)
         ptrs = [t.data_ptr() for t in d]
-        _lib.check(fn(self._get_handle(), *ptrs, *args(out), _torch_stream(torch, dev)), fn_name)
+        _lib.check(fn(self._get_handle(), *ptrs, *make_args(out), _torch_stream(torch, dev)), fn_name)
         return out[:n_out].cpu().numpy()
 
     def _mix(self, mixing_carrier_wave: np.ndarray, input_data: np.ndarray) -> np.ndarray:

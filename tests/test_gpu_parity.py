@@ -232,3 +232,28 @@ def test_stage_methods_match_reference_stages(taps_dir):
     assert len(ddc._decimate(ref[:5], 7)) == 0
     emax, el2 = rel_err(ddc._decimate(filt), ddc.run(x, 100e6))
     assert emax <= TOL_MAX and el2 <= TOL_L2, (emax, el2)
+
+
+@pytest.mark.parametrize("packed", [False, True])
+def test_odd_row_pitch_and_offset_outputs(taps_dir, packed):
+    """[streams, M] outputs with odd M put every other row on an odd complex64 element, and a caller may hand in a view
+    that starts 8 bytes off a 16-byte boundary: the fast-FIR epilogue picks its 16-byte store pairing per thread."""
+    n = 4096 * 40 + 256 + 64              # multiple of 64 (packed rows stay 16-byte aligned); M = 10245 is odd
+    ddc = _ddc(taps_dir, 16)
+    xs = np.stack([synth.digitiser_stream(n, 300 + s) for s in range(3)])
+    if packed:
+        x = torch.from_numpy(np.stack([synth.pack10(r) for r in xs])).cuda()
+    else:
+        x = torch.from_numpy(xs.astype(np.float32)).cuda()
+    m = ddc.out_len(n)
+    ref = np.stack([orc.ddc_reference(r.astype(np.float32), 100e6, ddc.ddc_filter_coeffs, 16, FS) for r in xs])
+    for pitch, off in ((m, 0), (m + 1, 0), (m + 1, 1), (m + 2, 1)):
+        flat = torch.zeros(3 * pitch + 4, dtype=torch.complex64, device="cuda")
+        out = flat[off: off + 3 * pitch].view(3, pitch)[:, :m]
+        ddc.run_tensor(x, 100e6, out=out, packed=packed)
+        assert "fast_fir" in ddc.last_variant, ddc.last_variant
+        emax, el2 = rel_err(out.cpu().numpy(), ref)
+        assert emax <= TOL_MAX and el2 <= TOL_L2, (pitch, off, emax, el2)
+        # nothing outside the M valid outputs of each row was written
+        pad = flat[off: off + 3 * pitch].view(3, pitch)[:, m:]
+        assert float(pad.abs().sum()) == 0.0 and float(flat[:off].abs().sum()) == 0.0

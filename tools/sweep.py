@@ -9,15 +9,19 @@ from scipy import signal
 
 HBM, FP32 = 6539.5, 74.4
 n = 1 << 26
+opts = [a.split("=") for a in sys.argv[1:] if "=" in a and not a.startswith("--")]       # key=value -> set_option
+dmin = int(next((a.split("=")[1] for a in sys.argv[1:] if a.startswith("--dmin=")), 4))
 x = torch.from_numpy(synth.digitiser_stream_fast(n, 1, block=1 << 22).astype(np.float32)).cuda().unsqueeze(0)
 tmp = tempfile.mkdtemp()
 print("| T | D | kernel | ms | Gsamples/s | GB/s (alg.) | % HBM (6539.5) | TFLOP/s | % FP32 (74.4) | binding roofline | % of binding |")
 print("|---:|---:|---|---:|---:|---:|---:|---:|---:|---|---:|")
 for t in (64, 128, 256, 512, 1024):
     for d in (4, 8, 16, 32, 64):
+        if d < dmin: continue
         csv = os.path.join(tmp, f"t{t}_{d}.csv")
         np.savetxt(csv, signal.firwin(t, 0.8 / d), fmt="%.18e")
         ddc = DigitalDownConverter(d, 1712e6, csv)
+        for k, v in opts: ddc.set_option(k, int(v))
         m = ddc.out_len(n)
         out = torch.empty((1, m), dtype=torch.complex64, device="cuda")
         for _ in range(3): ddc.run_tensor(x, 100e6, out=out)
