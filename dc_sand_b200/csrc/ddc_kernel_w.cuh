@@ -27,14 +27,23 @@ template <int D, int JT>
 struct WCfg : PCfg<D, JT, 1> {
     using B = PCfg<D, JT, 1>;
     static_assert(JT % 2 == 0 && B::R % 2 == 0, "fast FIR needs an even number of tap blocks and outputs per thread");
-    static constexpr int JH = JT / 2;              // tap pairs
+    // Long filters (JT = 32, 64, ...) run as NJG passes of JP = 16 tap blocks over the same staged chunk: pass jg reads the
+    // window that starts 16 jg blocks (= 16 jg / R thread-rows) further on; the ring geometry (halo rows, slot size) is
+    // PCfg's for the whole filter, the register window is the 16-block one.
+    static constexpr int JP = JT < 16 ? JT : 16;   // tap blocks per pass
+    static constexpr int NJG = JT / JP;            // passes
+    static_assert(JT % JP == 0, "long filters are padded to a multiple of 16 tap blocks");
+    static_assert(NJG == 1 || (JP % B::R == 0), "a pass must advance the window by whole thread-rows");
+    static constexpr int JH = JP / 2;              // tap pairs per pass
     static constexpr int RH = B::R / 2;            // output pairs per thread
-    static constexpr int NS = RH + JH - 1;         // entries of each derived sequence a thread touches
-    static constexpr int NTW = 3 * JH * D;         // complex taps passed to the kernel
+    static constexpr int NS = RH + JH - 1;         // entries of each derived sequence a thread touches per pass
+    static constexpr int NWP = B::R + JP - 1;      // blocks of the register window of one pass
+    static constexpr int WROWS = (NWP - 1) / B::R + 1;   // thread-rows a pass window spans
+    static constexpr int NTW = 3 * (JT / 2) * D;   // complex taps passed to the kernel
 };
 
 #ifndef DDCB200_W10_UNPACK_UNROLL
-#define DDCB200_W10_UNPACK_UNROLL 3
+#define DDCB200_W10_UNPACK_UNROLL 1   // 3 was measured slower (1.174 against 1.130 ms on 64 x 2^24 samples)
 #endif
 #ifndef DDCB200_W_PACKED_SUB
 #define DDCB200_W_PACKED_SUB 1
@@ -137,8 +146,8 @@ template <int D, int JT>
 __global__ void __launch_bounds__(WCfg<D, JT>::NWARPS * 32 + 32 * WCfg<D, JT>::NPROD, 1)
 ddc_fused_w_kernel(const __grid_constant__ RunParams p, const __grid_constant__ TapsParam<WCfg<D, JT>::NTW> taps) {
     using C = WCfg<D, JT>;
-    constexpr int ROW = C::ROW, R = C::R, NW = C::NW, NWARPS = C::NWARPS, NG = C::NGROUPS;
-    constexpr int NSLOT = C::NSLOT, RH = C::RH, NS = C::NS;
+    constexpr int ROW = C::ROW, R = C::R, NW = C::NWP, NWARPS = C::NWARPS, NG = C::NGROUPS;
+    constexpr int NSLOT = C::NSLOT, RH = C::RH, NS = C::NS, JP = C::JP, NJG = C::NJG;
     constexpr int WANT = C::TOT_ROWS * ROW;
     static_assert(2 * (NS - 1) + 2 == NW - 1, "window bookkeeping");
 
@@ -287,19 +296,48 @@ ddc_fused_w_kernel(const __grid_constant__ RunParams p, const __grid_constant__ 
                     for (int b = 0; b < NW; ++b)
                         w[b] = *reinterpret_cast<const float4*>(sbuf + rowoff[b / R] + (b % R) * D);
                     w_epilogue<R>(yprev, rot_thr, p.phase0_fx + (unsigned long long)prev_cc * chunk_dph, prev_m0, prev_o, prev_nout);
-                    w_fir_pg<D, JT, R>(w, tp, m0a, m1a, m2a);
+                    w_fir_pg<D, JP, R>(w, tp, m0a, m1a, m2a);
                     xoff = 4;
                     tp += 2;
                 }
+                if constexpr (NJG == 1) {
 #pragma unroll 1
-                for (int pg = 1; pg < C::V; ++pg, tp += 2) {
-                    asm volatile("" : "+r"(xoff));
-                    float4 w[NW];
+                    for (int pg = 1; pg < C::V; ++pg, tp += 2) {
+                        asm volatile("" : "+r"(xoff));
+                        float4 w[NW];
 #pragma unroll
-                    for (int b = 0; b < NW; ++b)
-                        w[b] = *reinterpret_cast<const float4*>(sbuf + xoff + rowoff[b / R] + (b % R) * D);
-                    xoff += 4;
-                    w_fir_pg<D, JT, R>(w, tp, m0a, m1a, m2a);
+                        for (int b = 0; b < NW; ++b)
+                            w[b] = *reinterpret_cast<const float4*>(sbuf + xoff + rowoff[b / R] + (b % R) * D);
+                        xoff += 4;
+                        w_fir_pg<D, JP, R>(w, tp, m0a, m1a, m2a);
+                    }
+                } else {
+                    // passes 1 .. NJG V - 1 share one loop body: pass = jg V + pg; the per-thread row offsets of tap group jg
+                    // are recomputed per pass (a dozen integer instructions against 384 FFMA2)
+                    int grow = g;   // first thread-row of the current pass window (opaque to the induction-variable optimiser)
+                    int pgi = 1;
+#pragma unroll 1
+                    for (int pass = 1; pass < NJG * C::V; ++pass) {
+                        asm volatile("" : "+r"(xoff), "+r"(grow));
+                        int ro[C::WROWS];
+#pragma unroll
+                        for (int h = 0; h < C::WROWS; ++h) ro[h] = ((grow + h) / C::SROWS) * C::SRP + ((grow + h) % C::SROWS) * ROW;
+                        float4 w[NW];
+#pragma unroll
+                        for (int b = 0; b < NW; ++b)
+                            w[b] = *reinterpret_cast<const float4*>(sbuf + xoff + ro[b / R] + (b % R) * D);
+                        w_fir_pg<D, JP, R>(w, tp, m0a, m1a, m2a);
+                        // next pass: next phase group, or phase group 0 of the next tap group
+                        ++pgi;
+                        xoff += 4;
+                        tp += 2;
+                        if (pgi == C::V) {
+                            pgi = 0;
+                            xoff = 0;
+                            grow += JP / R;
+                            tp += 3 * (JP / 2) * (D / 2) - 2 * C::V;   // tap set (i = JP/2 (jg+1), seq 0), phase group 0
+                        }
+                    }
                 }
             }
             __syncwarp();

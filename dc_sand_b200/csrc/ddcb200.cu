@@ -84,6 +84,10 @@ struct ddcb200 {
     unsigned long long* d_dbg = nullptr;   // diagnostic counters (option "dbg_counters")
     std::string last_variant = "none";
     bool smem_attr_set = false;
+    // folded fast-FIR taps of the last (step, jt, D): streaming callers repeat the same step call after call
+    std::vector<float2> wt_cache;
+    double wt_step = 0.0;
+    int wt_jt = 0, wt_d = 0;
 };
 
 namespace {
@@ -129,6 +133,18 @@ void make_wtaps(const ddcb200* h, double step, int jt, int D, float2* out) {
             out[(3 * i + 1) * D + d] = make_float2((float)(er + orr), (float)(ei + oi));
             out[(3 * i + 2) * D + d] = make_float2((float)orr, (float)oi);
         }
+}
+
+// cached front end of make_wtaps (invalidated by set_taps / set_decimation through wt_jt = 0)
+const float2* cached_wtaps(ddcb200* h, double step, int jt, int D) {
+    if (h->wt_jt != jt || h->wt_d != D || h->wt_step != step || h->wt_cache.size() != (size_t)(3 * (jt / 2) * D)) {
+        h->wt_cache.resize((size_t)(3 * (jt / 2) * D));
+        make_wtaps(h, step, jt, D, h->wt_cache.data());
+        h->wt_step = step;
+        h->wt_jt = jt;
+        h->wt_d = D;
+    }
+    return h->wt_cache.data();
 }
 
 unsigned long long to_fx64(double frac01) {
@@ -302,7 +318,7 @@ int launch_w(ddcb200* h, RunParams& p, cudaStream_t st, double step) {
         attr_set[h->device] = true;
     }
     TapsParam<C::NTW> tp;
-    make_wtaps(h, step, JT, D, reinterpret_cast<float2*>(tp.c2));
+    std::memcpy(tp.c2, cached_wtaps(h, step, JT, D), sizeof(float2) * (size_t)C::NTW);
     const long long grid = std::min<long long>(p.total_tiles, h->sm_count);
     kern<<<(unsigned)grid, C::NWARPS * 32 + 32 * C::NPROD, smem, st>>>(p, tp);
     CUDA_TRY(cudaGetLastError());
@@ -318,8 +334,14 @@ int launch_w_j(ddcb200* h, RunParams& p, cudaStream_t st, double step, int jt) {
     switch (jt) {
         case 4: return launch_w<D, 4>(h, p, st, step);
         case 8: return launch_w<D, 8>(h, p, st, step);
-        default: return launch_w<D, 16>(h, p, st, step);
+        case 16: return launch_w<D, 16>(h, p, st, step);
+        default: break;
     }
+    if constexpr (D == 16) {   // long filters: passes of 16 tap blocks (T <= 1024)
+        if (jt == 32) return launch_w<D, 32>(h, p, st, step);
+        if (jt == 64) return launch_w<D, 64>(h, p, st, step);
+    }
+    return fail(DDCB200_EINVAL, "fast-FIR kernel: unsupported tap-block count %d at D = %d", jt, D);
 }
 
 template <int D, int JT>
@@ -333,7 +355,7 @@ int launch_w10(ddcb200* h, RunParams& p, cudaStream_t st, double step) {
         attr_set[h->device] = true;
     }
     TapsParam<C::NTW> tp;
-    make_wtaps(h, step, JT, D, reinterpret_cast<float2*>(tp.c2));
+    std::memcpy(tp.c2, cached_wtaps(h, step, JT, D), sizeof(float2) * (size_t)C::NTW);
     const long long grid = std::min<long long>(p.total_tiles, h->sm_count);
     kern<<<(unsigned)grid, C::NWARPS * 32 + 32 * C::NPROD, smem, st>>>(p, tp);
     CUDA_TRY(cudaGetLastError());
@@ -432,8 +454,6 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         (T + D - 1) / D <= 16 && h->force_variant != 1) {
         const int Jp = (T + D - 1) / D;
         const int jt = Jp <= 4 ? 4 : (Jp <= 8 ? 8 : 16);
-        std::vector<float2> ctp((size_t)jt * D);
-        make_ctaps(h, step, jt * D, ctp.data());
         const long long chunk_out = 32LL * (128 / D);
         p.tiles_per_stream = (M + chunk_out - 1) / chunk_out;
         p.total_tiles = p.tiles_per_stream * n_streams;
@@ -448,6 +468,8 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
                 default: return launch_w10_j<64>(h, p, st, step, jt);
             }
         }
+        std::vector<float2> ctp((size_t)jt * D);
+        make_ctaps(h, step, jt * D, ctp.data());
         switch (D) {
             case 16: return launch_p10_j<16>(h, p, ctp.data(), st, jt);
             case 32: return launch_p10_j<32>(h, p, ctp.data(), st, jt);
@@ -456,13 +478,12 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
     }
 
     // ---- kernel P (phase-major, R = 128/D outputs per thread): short polyphase branches, J = ceil(T/D) <= 16 ------
-    if (aligned_f32(d_in, in_stride, packed) && (D == 16 || D == 32 || D == 64) && (T + D - 1) / D <= 16 &&
+    const bool long_w = D == 16 && (T + D - 1) / D > 16 && (T + D - 1) / D <= 64 && (h->force_variant == 0 || h->force_variant == 7);
+    if (aligned_f32(d_in, in_stride, packed) && (D == 16 || D == 32 || D == 64) && ((T + D - 1) / D <= 16 || long_w) &&
         (h->force_variant == 0 || (h->force_variant >= 5 && h->force_variant <= 8))) {
         const int ksp = (h->force_variant == 6) ? 2 : 1;   // option "variant": 5 (= auto) one warp per chunk, 6 = two (slower)
         const int Jp = (T + D - 1) / D;
-        const int jt = Jp <= 4 ? 4 : (Jp <= 8 ? 8 : 16);
-        std::vector<float2> ctp((size_t)jt * D);
-        make_ctaps(h, step, jt * D, ctp.data());
+        const int jt = Jp <= 4 ? 4 : (Jp <= 8 ? 8 : (Jp <= 16 ? 16 : (Jp <= 32 ? 32 : 64)));
         const long long chunk_out = 32LL * (128 / D);   // PCfg::CHUNK_OUT
         p.tiles_per_stream = (M + chunk_out - 1) / chunk_out;
         p.total_tiles = p.tiles_per_stream * n_streams;
@@ -479,6 +500,8 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
                 default: return launch_w_j<64>(h, p, st, step, jt);
             }
         }
+        std::vector<float2> ctp((size_t)jt * D);
+        make_ctaps(h, step, jt * D, ctp.data());
         if (h->force_variant == 0 || h->force_variant == 8) {   // deferred-epilogue variant
             switch (D) {
                 case 16: return launch_pd_j<16>(h, p, ctp.data(), st, jt);
@@ -645,6 +668,7 @@ int ddcb200_set_taps(ddcb200_t* h, const double* taps, int n_taps) {
     if (!(s != 0.0) || !std::isfinite(s)) return fail(DDCB200_EINVAL, "set_taps: sum of taps is %g", s);
     h->taps.assign(taps, taps + n_taps);
     h->taps_sum = s;
+    h->wt_jt = 0;   // invalidate the folded-tap cache
     return DDCB200_OK;
 }
 
