@@ -29,6 +29,18 @@ SIGNATURES = {
                                        C.c_void_p, C.c_int64]),
     "ddcb200_run_host_packed10": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double,
                                             C.c_int64, C.c_void_p, C.c_int64]),
+    "ddcb200_cwg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_double,
+                              C.c_int64, C.c_int, C.c_double, C.c_uint64, C.c_void_p]),
+    "ddcb200_session_open": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.POINTER(C.c_void_p)]),
+    "ddcb200_session_close": (None, [C.c_void_p]),
+    "ddcb200_session_reset": (C.c_int, [C.c_void_p, C.c_int64]),
+    "ddcb200_session_pending": (C.c_int64, [C.c_void_p]),
+    "ddcb200_session_position": (C.c_int64, [C.c_void_p]),
+    "ddcb200_session_out_len": (C.c_int64, [C.c_void_p, C.c_int64]),
+    "ddcb200_session_push_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                           C.POINTER(C.c_int64), C.c_void_p]),
+    "ddcb200_session_push_host_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                                C.POINTER(C.c_int64)]),
     "ddcb200_host_alloc": (C.c_void_p, [C.c_size_t]),
     "ddcb200_host_free": (None, [C.c_void_p]),
     "ddcb200_sync": (C.c_int, [C.c_void_p]),

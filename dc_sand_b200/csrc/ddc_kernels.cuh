@@ -107,6 +107,76 @@ __global__ void decimate_c64_kernel(const float2* __restrict__ z, long long offs
 }
 
 // =============================================================================================================
+// Carrier-wave / test-signal generator on the device (reference: feng/ddc/src/cwg.py:6-70, the test-vector source of the
+// reference's own tests).  sample n = cw_scale * exp(-j 2 pi (phase0 + n step)) [+ noise on the real part]
+//   noise_mode 0: none
+//   noise_mode 1: noise_scale * truncated normal on [-1, 1], sigma 0.5        (cwg._generate_noise, cwg.py:47-70)
+//   noise_mode 2: noise_scale * N(0, 1), then round-to-nearest and clip to the 10-bit range [-512, 511]   (digitiser model)
+// Noise comes from Philox4x32-10 keyed by (seed, stream) with the sample index as counter: reproducible, order-free.
+// =============================================================================================================
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+
+// two independent N(0,1) from two 32-bit words (Box-Muller); u1 in (0, 1]
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+    const float u1 = ((float)(a >> 8) + 1.0f) * (1.0f / 16777216.0f);
+    const float u2 = (float)(b >> 8) * (1.0f / 16777216.0f);
+    const float rad = sqrtf(-2.0f * __logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    return make_float2(rad * cs, rad * sn);
+}
+
+template <bool COMPLEX>
+__global__ void cwg_kernel(void* __restrict__ out, long long n, long long out_stride, float cw_scale, unsigned long long step_fx,
+                           unsigned long long phase0_fx, int noise_mode, float noise_scale, unsigned long long seed) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned stream = blockIdx.y;
+    if (i >= n) return;
+    const float2 cw = ddck::nco_rot(phase0_fx + (unsigned long long)i * step_fx);   // exp(-j 2 pi phase)
+    float re = cw_scale * cw.x, im = cw_scale * cw.y;
+    if (noise_mode != 0) {
+        const uint2 key = make_uint2((uint32_t)seed ^ (stream * 0x9E3779B9u), (uint32_t)(seed >> 32) + stream);
+        float g = 0.f;
+        if (noise_mode == 1) {
+            // truncated normal by rejection (95.4 % acceptance); attempt number in counter word w
+            bool ok = false;
+            for (uint32_t att = 0; att < 16 && !ok; ++att) {
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)((unsigned long long)i >> 32), 0x7A11u, att), key);
+                const float2 z0 = box_muller(r.x, r.y), z1 = box_muller(r.z, r.w);
+                const float c[4] = {0.5f * z0.x, 0.5f * z0.y, 0.5f * z1.x, 0.5f * z1.y};
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (!ok && fabsf(c[k]) <= 1.0f) {
+                        g = c[k];
+                        ok = true;
+                    }
+            }
+            re += noise_scale * g;
+        } else {
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)((unsigned long long)i >> 32), 0xD161u, 0u), key);
+            g = box_muller(r.x, r.y).x;
+            re = fminf(fmaxf(rintf(re + noise_scale * g), -512.f), 511.f);
+            im = 0.f;
+        }
+    }
+    if (COMPLEX)
+        reinterpret_cast<float2*>(out)[(long long)stream * out_stride + i] = make_float2(re, im);
+    else
+        reinterpret_cast<float*>(out)[(long long)stream * out_stride + i] = re;
+}
+
+// =============================================================================================================
 // Fused persistent kernel
 // =============================================================================================================
 // Shared-memory layout of one pipeline stage.  A "thread-row" is the ROW = R*D float32 samples that produce R

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -843,6 +844,28 @@ int ddcb200_decimate_c64(ddcb200_t* h, const ddcb200_c64* d_in, int64_t n_in, in
     return DDCB200_OK;
 }
 
+int ddcb200_cwg(ddcb200_t* h, void* d_out, int64_t num_samples, int64_t n_streams, int64_t out_stride, int is_complex,
+                double cw_scale, double phase_step_cycles, double phase0_cycles, int64_t sample_offset, int noise_mode,
+                double noise_scale, uint64_t seed, void* cuda_stream) {
+    if (!h || !d_out || num_samples <= 0 || n_streams <= 0 || n_streams > 65535 || out_stride < num_samples)
+        return fail(DDCB200_EINVAL, "cwg: bad arguments");
+    if (noise_mode < 0 || noise_mode > 2) return fail(DDCB200_EINVAL, "cwg: noise_mode must be 0, 1 or 2");
+    DeviceGuard g(h->device);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    const unsigned long long step_fx = to_fx64(phase_step_cycles - std::floor(phase_step_cycles));
+    const unsigned long long ph0 = to_fx64(phase0_cycles - std::floor(phase0_cycles)) + phase_of(phase_step_cycles, sample_offset);
+    dim3 grid((unsigned)((num_samples + 255) / 256), (unsigned)n_streams);
+    if (is_complex)
+        cwg_kernel<true><<<grid, 256, 0, st>>>(d_out, num_samples, out_stride, (float)cw_scale, step_fx, ph0, noise_mode,
+                                               (float)noise_scale, seed);
+    else
+        cwg_kernel<false><<<grid, 256, 0, st>>>(d_out, num_samples, out_stride, (float)cw_scale, step_fx, ph0, noise_mode,
+                                                (float)noise_scale, seed);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return DDCB200_OK;
+}
+
 int ddcb200_run_host_f32(ddcb200_t* h, const float* h_in, int64_t n_samples, int64_t n_streams, int64_t in_stride,
                          double step, int64_t sample_offset, ddcb200_c64* h_out, int64_t out_stride) {
     if (!h) return fail(DDCB200_EINVAL, "null handle");
@@ -935,6 +958,187 @@ int ddcb200_set_option(ddcb200_t* h, const char* key, int64_t value) {
         return DDCB200_OK;
     }
     return fail(DDCB200_EINVAL, "unknown option '%s'", key);
+}
+
+// ================================================================================================================
+// Streaming sessions: a continuous digitiser stream arrives in arbitrary pieces; the session keeps the
+// last T-D .. T-1 samples of every stream in device memory so that no output is lost or duplicated at push boundaries,
+// and the absolute sample index so that the NCO phase is continuous.
+// ================================================================================================================
+struct ddcb200_session {
+    ddcb200* h = nullptr;
+    int64_t n_streams = 0, max_chunk = 0;
+    double step = 0.0;
+    int64_t carry = 0;     // samples of every stream waiting at the head of work[cur]
+    int64_t abs0 = 0;      // absolute index of the first carried sample (always a multiple of D)
+    int64_t pitch = 0;     // floats per stream row of a work buffer (multiple of 4: rows stay 16-byte aligned)
+    int64_t out_cap = 0;   // outputs per stream a push of max_chunk samples can produce
+    float* work[2] = {};
+    ddcb200_c64* dout[2] = {};
+    cudaEvent_t ev_in[2] = {}, ev_k[2] = {}, ev_out[2] = {};
+    cudaEvent_t ev_user = nullptr;   // end of the last asynchronous device push (on the caller's stream)
+    bool user_pending = false;
+    int cur = 0;
+};
+
+namespace {
+// One piece (n <= max_chunk samples per stream, already in work[cur] behind the carry): run the DDC over carry + n samples
+// into d_out and move the unconsumed tail to the head of the other work buffer.  Everything on `st`.
+int stream_step(ddcb200_session* s, int64_t n, ddcb200_c64* d_out, int64_t out_stride, int64_t* n_out, cudaStream_t st) {
+    ddcb200* h = s->h;
+    const int T = (int)h->taps.size(), D = h->decim;
+    const int64_t have = s->carry + n;
+    int64_t m = 0;
+    if (have >= T) {
+        m = (have - T) / D + 1;
+        int rc = run_device(h, s->work[s->cur], false, have, s->n_streams, s->pitch, s->step, s->abs0, d_out, out_stride, st);
+        if (rc) return rc;
+    }
+    const int64_t used = m * D, rest = have - used;
+    if (rest > 0 && used > 0)
+        CUDA_TRY(cudaMemcpy2DAsync(s->work[s->cur ^ 1], (size_t)s->pitch * 4, s->work[s->cur] + used, (size_t)s->pitch * 4,
+                                   (size_t)rest * 4, (size_t)s->n_streams, cudaMemcpyDeviceToDevice, st));
+    if (used > 0) s->cur ^= 1;
+    s->carry = rest;
+    s->abs0 += used;
+    *n_out = m;
+    return DDCB200_OK;
+}
+}  // namespace
+
+int ddcb200_session_open(ddcb200_t* h, int64_t n_streams, int64_t max_chunk_samples, double phase_step_cycles,
+                        ddcb200_session_t** out) {
+    if (!h || !out || n_streams <= 0 || n_streams > 65535 || max_chunk_samples <= 0)
+        return fail(DDCB200_EINVAL, "session_open: bad arguments");
+    *out = nullptr;
+    DeviceGuard g(h->device);
+    const int T = (int)h->taps.size(), D = h->decim;
+    if (T < D) return fail(DDCB200_EINVAL, "session_open: streaming needs n_taps (%d) >= decimation (%d)", T, D);
+    auto* s = new (std::nothrow) ddcb200_session();
+    if (!s) return fail(DDCB200_ENOMEM, "session_open: out of host memory");
+    s->h = h;
+    s->n_streams = n_streams;
+    s->max_chunk = std::max<int64_t>(max_chunk_samples, (int64_t)T);
+    s->step = phase_step_cycles;
+    s->pitch = ((int64_t)(T + D) + s->max_chunk + 3) / 4 * 4;
+    s->out_cap = (s->max_chunk + T + D) / D + 1;
+    for (int i = 0; i < 2; ++i) {
+        if (cudaMalloc(&s->work[i], (size_t)s->pitch * 4 * (size_t)n_streams) != cudaSuccess ||
+            cudaMalloc(&s->dout[i], (size_t)s->out_cap * sizeof(ddcb200_c64) * (size_t)n_streams) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->ev_k[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->ev_out[i], cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            ddcb200_session_close(s);
+            return fail(DDCB200_ENOMEM, "session_open: device allocation failed (%lld streams x %lld samples)",
+                        (long long)n_streams, (long long)s->pitch);
+        }
+    }
+    if (cudaEventCreateWithFlags(&s->ev_user, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        ddcb200_session_close(s);
+        return fail(DDCB200_ECUDA, "session_open: event creation failed");
+    }
+    *out = s;
+    return DDCB200_OK;
+}
+
+void ddcb200_session_close(ddcb200_session_t* s) {
+    if (!s) return;
+    DeviceGuard g(s->h->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; ++i) {
+        if (s->work[i]) cudaFree(s->work[i]);
+        if (s->dout[i]) cudaFree(s->dout[i]);
+        if (s->ev_in[i]) cudaEventDestroy(s->ev_in[i]);
+        if (s->ev_k[i]) cudaEventDestroy(s->ev_k[i]);
+        if (s->ev_out[i]) cudaEventDestroy(s->ev_out[i]);
+    }
+    if (s->ev_user) cudaEventDestroy(s->ev_user);
+    delete s;
+}
+
+int ddcb200_session_reset(ddcb200_session_t* s, int64_t first_sample_index) {
+    if (!s || first_sample_index < 0) return fail(DDCB200_EINVAL, "session_reset: bad arguments");
+    if (first_sample_index % s->h->decim) return fail(DDCB200_EINVAL, "session_reset: index must be a multiple of the decimation");
+    s->carry = 0;
+    s->abs0 = first_sample_index;
+    return DDCB200_OK;
+}
+
+int64_t ddcb200_session_pending(ddcb200_session_t* s) { return s ? s->carry : 0; }
+int64_t ddcb200_session_position(ddcb200_session_t* s) { return s ? s->abs0 + s->carry : 0; }
+
+int64_t ddcb200_session_out_len(ddcb200_session_t* s, int64_t n_samples) {
+    if (!s || n_samples < 0) return 0;
+    const int64_t have = s->carry + n_samples, T = (int64_t)s->h->taps.size();
+    return have >= T ? (have - T) / s->h->decim + 1 : 0;
+}
+
+int ddcb200_session_push_f32(ddcb200_session_t* s, const float* d_in, int64_t n_samples, int64_t in_stride, ddcb200_c64* d_out,
+                            int64_t out_stride, int64_t* n_out, void* cuda_stream) {
+    if (!s || !d_in || !n_out || n_samples <= 0) return fail(DDCB200_EINVAL, "session_push: bad arguments");
+    if (n_samples > s->max_chunk) return fail(DDCB200_EINVAL, "session_push: %lld samples > max_chunk_samples %lld",
+                                              (long long)n_samples, (long long)s->max_chunk);
+    const int64_t m = ddcb200_session_out_len(s, n_samples);
+    if (m > 0 && (!d_out || out_stride < m)) return fail(DDCB200_EINVAL, "session_push: output too small for %lld outputs", (long long)m);
+    DeviceGuard g(s->h->device);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : s->h->stream;
+    CUDA_TRY(cudaMemcpy2DAsync(s->work[s->cur] + s->carry, (size_t)s->pitch * 4, d_in, (size_t)in_stride * 4, (size_t)n_samples * 4,
+                               (size_t)s->n_streams, cudaMemcpyDeviceToDevice, st));
+    int rc = stream_step(s, n_samples, d_out, out_stride, n_out, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(s->ev_user, st));
+    s->user_pending = true;
+    return DDCB200_OK;
+}
+
+int ddcb200_session_push_host_f32(ddcb200_session_t* s, const float* h_in, int64_t n_samples, int64_t in_stride, ddcb200_c64* h_out,
+                                 int64_t out_stride, int64_t* n_out) {
+    if (!s || !h_in || !n_out || n_samples <= 0) return fail(DDCB200_EINVAL, "session_push_host: bad arguments");
+    const int64_t m_total = ddcb200_session_out_len(s, n_samples);
+    if (m_total > 0 && (!h_out || out_stride < m_total)) return fail(DDCB200_EINVAL, "session_push_host: output too small");
+    ddcb200* h = s->h;
+    DeviceGuard g(h->device);
+    // Pieces of max_chunk samples, two work buffers deep: the H2D copy of piece i + 1 (copy_in stream) runs under the
+    // kernel of piece i (compute stream), the D2H copy of its outputs on copy_out.
+    if (s->user_pending) {   // an asynchronous device push may still be using the work buffers on the caller's stream
+        CUDA_TRY(cudaStreamWaitEvent(h->copy_in, s->ev_user, 0));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, s->ev_user, 0));
+        s->user_pending = false;
+    }
+    int64_t done = 0, m_done = 0;
+    bool rec_k[2] = {false, false}, rec_out[2] = {false, false};
+    while (done < n_samples) {
+        const int64_t n = std::min<int64_t>(s->max_chunk, n_samples - done);
+        const int b = s->cur;
+        if (rec_k[b]) CUDA_TRY(cudaStreamWaitEvent(h->copy_in, s->ev_k[b], 0));     // last kernel / tail copy reading work[b]
+        CUDA_TRY(cudaMemcpy2DAsync(s->work[b] + s->carry, (size_t)s->pitch * 4, h_in + done, (size_t)in_stride * 4, (size_t)n * 4,
+                                   (size_t)s->n_streams, cudaMemcpyHostToDevice, h->copy_in));
+        CUDA_TRY(cudaEventRecord(s->ev_in[b], h->copy_in));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, s->ev_in[b], 0));
+        if (rec_out[b]) CUDA_TRY(cudaStreamWaitEvent(h->stream, s->ev_out[b], 0));  // dout[b] has been copied out
+        int64_t m = 0;
+        int rc = stream_step(s, n, s->dout[b], s->out_cap, &m, h->stream);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(s->ev_k[b], h->stream));
+        rec_k[b] = true;
+        if (m > 0) {
+            CUDA_TRY(cudaStreamWaitEvent(h->copy_out, s->ev_k[b], 0));
+            CUDA_TRY(cudaMemcpy2DAsync(h_out + m_done, (size_t)out_stride * sizeof(ddcb200_c64), s->dout[b],
+                                       (size_t)s->out_cap * sizeof(ddcb200_c64), (size_t)m * sizeof(ddcb200_c64),
+                                       (size_t)s->n_streams, cudaMemcpyDeviceToHost, h->copy_out));
+            CUDA_TRY(cudaEventRecord(s->ev_out[b], h->copy_out));
+            rec_out[b] = true;
+        }
+        done += n;
+        m_done += m;
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->copy_out));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->copy_in));
+    *n_out = m_done;
+    return DDCB200_OK;
 }
 
 }  // extern "C"

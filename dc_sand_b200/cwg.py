@@ -55,3 +55,58 @@ def _generate_noise(scale: float, array_length: int, rng: np.random.Generator | 
         out[filled : filled + take] = draw[:take]
         filled += take
     return scale * out.astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Device-side generator: the same carrier wave produced directly in HBM by libddcb200.so
+# (ddcb200_cwg), for inputs that should never be staged through the host.
+# ---------------------------------------------------------------------------------------------------------------------
+_gen_handles: dict = {}
+
+
+def _generator_handle(device: int):
+    """A minimal native handle (one unit tap) per device: ddcb200_cwg only needs its device and stream."""
+    import ctypes as C
+
+    from . import _lib
+
+    if device not in _gen_handles:
+        h = C.c_void_p()
+        one = (C.c_double * 1)(1.0)
+        _lib.check(_lib.load().ddcb200_create(C.byref(h), int(device), one, 1, 1), "ddcb200_create")
+        _gen_handles[device] = h
+    return _gen_handles[device]
+
+
+def generate_carrier_wave_gpu(cw_scale: float, freq: float, sampling_frequency: float, num_samples: int, noise_scale: float,
+                              complex: bool, seed: int = 0, device: int = 0, n_streams: int | None = None,
+                              sample_offset: int = 0, digitise: bool = False, phase0_cycles: float = 0.0, out=None,
+                              total_samples: int | None = None):
+    """`generate_carrier_wave` on the GPU: returns a torch CUDA tensor, float32 (complex=False) or complex64, of shape
+    [num_samples] (or [n_streams, num_samples]; stream s draws its noise from key (seed, s)).
+
+    The tone follows the reference's phase law exactly (cwg.py:31-36); the noise is the reference's truncated normal
+    (sigma 0.5 on [-1, 1], cwg.py:47-70) from a seeded Philox counter RNG -- the reference's own draw is unseeded, so only
+    its statistics can be matched.  digitise=True switches to the digitiser model of SURVEY 8d instead: real part plus
+    noise_scale * N(0, 1), rounded and clipped to the 10-bit range."""
+    import torch
+
+    from . import _lib
+    from .ddc import _torch_stream
+
+    dev = torch.device("cuda", int(device))
+    s = 1 if n_streams is None else int(n_streams)
+    if out is None:
+        out = torch.empty((s, int(num_samples)), dtype=torch.complex64 if complex else torch.float32, device=dev)
+    elif out.dim() != 2 or out.shape != (s, int(num_samples)) or out.stride(1) != 1:
+        raise ValueError("out must be [n_streams, num_samples] with contiguous rows")
+    # a piece of a longer wave: phase law of the whole (total_samples), starting at sample_offset
+    step = phase_step_cycles(int(num_samples if total_samples is None else total_samples), freq, sampling_frequency)
+    mode = 0 if noise_scale == 0 else (2 if digitise else 1)
+    _lib.check(
+        _lib.load().ddcb200_cwg(_generator_handle(int(device)), out.data_ptr(), int(num_samples), s, out.stride(0), int(bool(complex)),
+                                float(cw_scale), step, float(phase0_cycles), int(sample_offset), mode, float(noise_scale),
+                                int(seed) & 0xFFFFFFFFFFFFFFFF, _torch_stream(torch, dev)),
+        "ddcb200_cwg",
+    )
+    return out[0] if n_streams is None else out

@@ -105,6 +105,17 @@ int ddcb200_fir_c64(ddcb200_t* handle, const ddcb200_c64* d_in, int64_t n_in, dd
 int ddcb200_decimate_c64(ddcb200_t* handle, const ddcb200_c64* d_in, int64_t n_in, int64_t offset, ddcb200_c64* d_out,
                          void* cuda_stream);
 
+/* ---- test-signal generator on the device ----------------------------------------------------------------------------
+ * Replaces cwg.generate_carrier_wave (feng/ddc/src/cwg.py:6-44), the reference's test-vector source, for inputs that
+ * should never touch the host: sample n of stream s = cw_scale * exp(-j 2 pi (phase0_cycles + (sample_offset + n) *
+ * phase_step_cycles)), float32 real part (is_complex = 0) or complex64.  noise_mode 0: none; 1: + noise_scale *
+ * truncated normal on [-1, 1], sigma 0.5, on the real part (cwg.py:47-70; the reference's draw is unseeded, this one is
+ * Philox4x32-10 keyed by (seed, stream), counter = sample index); 2: digitiser model, real part + noise_scale * N(0,1),
+ * rounded and clipped to [-512, 511].  phase_step_cycles = int(N f / fs) / (N - 1) reproduces the reference's linspace. */
+int ddcb200_cwg(ddcb200_t* handle, void* d_out, int64_t num_samples, int64_t n_streams, int64_t out_stride, int is_complex,
+                double cw_scale, double phase_step_cycles, double phase0_cycles, int64_t sample_offset, int noise_mode,
+                double noise_scale, uint64_t seed, void* cuda_stream);
+
 /* ---- host-buffer entry points (what DigitalDownConverter.run binds to) -------------------------------------
  * Replace DigitalDownConverter.run (ddc.py:121-188) for host arrays: time-chunked, double-buffered
  * H2D -> fused kernel -> D2H on two CUDA streams, synchronous on return.  Pinned host memory (see
@@ -116,6 +127,26 @@ int ddcb200_run_host_f32(ddcb200_t* handle, const float* h_in, int64_t n_samples
 int ddcb200_run_host_packed10(ddcb200_t* handle, const uint8_t* h_in, int64_t n_samples, int64_t n_streams,
                               int64_t in_stride_bytes, double phase_step_cycles, int64_t sample_offset,
                               ddcb200_c64* h_out, int64_t out_stride);
+
+/* ---- streaming sessions -------------------------------------------------------------------------------------------
+ * The reference processes one finite array per run() (ddc.py:121); a digitiser delivers an endless stream (cf. the
+ * reference's ibverbs receiver, ibverbs_sample_project/ibverbs_rx.c:282-327).  A session carries the last T-D .. T-1
+ * samples of every stream and the absolute sample index across pushes, so the concatenated outputs of any sequence of
+ * pushes equal one run() over the concatenated input (same NCO phase law: pass the phase_step_cycles of that run()).
+ * push_f32: device pointers, asynchronous on `cuda_stream`; push_host_f32: host pointers, pieces of max_chunk_samples
+ * double-buffered (H2D of piece i+1 under the kernel of piece i), synchronous on return.  *n_out = outputs per stream. */
+typedef struct ddcb200_session ddcb200_session_t;
+int ddcb200_session_open(ddcb200_t* handle, int64_t n_streams, int64_t max_chunk_samples, double phase_step_cycles,
+                        ddcb200_session_t** out);
+void ddcb200_session_close(ddcb200_session_t* s);
+int ddcb200_session_reset(ddcb200_session_t* s, int64_t first_sample_index);
+int64_t ddcb200_session_pending(ddcb200_session_t* s);    /* samples carried per stream */
+int64_t ddcb200_session_position(ddcb200_session_t* s);   /* absolute index of the next sample to be pushed */
+int64_t ddcb200_session_out_len(ddcb200_session_t* s, int64_t n_samples);   /* outputs the next push of n_samples will give */
+int ddcb200_session_push_f32(ddcb200_session_t* s, const float* d_in, int64_t n_samples, int64_t in_stride,
+                            ddcb200_c64* d_out, int64_t out_stride, int64_t* n_out, void* cuda_stream);
+int ddcb200_session_push_host_f32(ddcb200_session_t* s, const float* h_in, int64_t n_samples, int64_t in_stride,
+                                 ddcb200_c64* h_out, int64_t out_stride, int64_t* n_out);
 
 /* Pinned host memory helpers (the reference's prototype uses cuda.pagelocked_empty, ddc_host_gpu.py:45-58). */
 void* ddcb200_host_alloc(size_t bytes);

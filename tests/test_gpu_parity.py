@@ -257,3 +257,73 @@ def test_odd_row_pitch_and_offset_outputs(taps_dir, packed):
         # nothing outside the M valid outputs of each row was written
         pad = flat[off: off + 3 * pitch].view(3, pitch)[:, m:]
         assert float(pad.abs().sum()) == 0.0 and float(flat[:off].abs().sum()) == 0.0
+
+
+def test_streaming_pushes_equal_one_shot_run(taps_dir):
+    """A stream pushed in ragged pieces (shorter than T, not multiples of D, longer than max_chunk) gives the outputs of
+    one run() over the whole input: the session carries the T-D .. T-1 sample history and the NCO phase."""
+    from dc_sand_b200 import DDCStream
+
+    n = 300_007
+    x = synth.digitiser_stream(n, 55).astype(np.float32)
+    ddc = _ddc(taps_dir, 16)
+    y_ref = orc.ddc_reference(x, 100e6, ddc.ddc_filter_coeffs, 16, FS)
+    with DDCStream(ddc, 100e6, max_chunk=40_000, total_samples=n) as st:
+        cuts = [0, 100, 250, 251, 4347, 4352, 60_001, 190_000, 190_016, 299_999, n]   # includes a piece > max_chunk
+        parts = [st.push(x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+        assert len(parts[0]) == 0 and len(parts[1]) == 0          # fewer than T samples so far
+        y = np.concatenate(parts)
+        assert st.position == n and st.pending == n - len(y) * 16
+    assert y.shape == y_ref.shape
+    emax, el2 = rel_err(y, y_ref)
+    assert emax <= TOL_MAX and el2 <= TOL_L2, (emax, el2)
+
+
+def test_streaming_device_tensors_many_streams(taps_dir):
+    """Device-resident pushes (asynchronous, torch stream) for 3 streams, then a host push on the same session."""
+    from dc_sand_b200 import DDCStream
+
+    n = 120_000
+    xs = np.stack([synth.digitiser_stream(n, 70 + s) for s in range(3)]).astype(np.float32)
+    ddc = _ddc(taps_dir, 16)
+    ref = np.stack([orc.ddc_reference(r, 100e6, ddc.ddc_filter_coeffs, 16, FS) for r in xs])
+    xd = torch.from_numpy(xs).cuda()
+    with DDCStream(ddc, 100e6, n_streams=3, max_chunk=50_000, total_samples=n) as st:
+        a = st.push_tensor(xd[:, :33_333].contiguous()).cpu().numpy()
+        b = st.push_tensor(xd[:, 33_333:80_000]).cpu().numpy()          # a strided view: rows are 120000 apart
+        c = st.push(xs[:, 80_000:])
+    y = np.concatenate([a, b, c], axis=1)
+    emax, el2 = rel_err(y, ref)
+    assert y.shape == ref.shape and emax <= TOL_MAX and el2 <= TOL_L2, (y.shape, emax, el2)
+
+
+def test_true_nco_step_without_total_samples(taps_dir):
+    """Without total_samples the stream uses the exact NCO step fc / fs (what the reference's linspace law tends to)."""
+    from dc_sand_b200 import DDCStream
+
+    n = 1 << 17
+    x = synth.digitiser_stream(n, 5).astype(np.float32)
+    ddc = _ddc(taps_dir, 16)
+    with DDCStream(ddc, 100e6) as st:
+        y = np.concatenate([st.push(x[: n // 3]), st.push(x[n // 3:])])
+    ref = orc.ddc_windowed_f64(x, 0, len(y), 100e6 / FS, ddc.ddc_filter_coeffs, 16)
+    emax, el2 = rel_err(y, ref)
+    assert emax <= TOL_MAX and el2 <= TOL_L2, (emax, el2)
+
+
+def test_runtime_tap_reload_and_narrowband_mode(taps_dir):
+    """the second shipped filter (ddc_coeff_53MHz.csv) with a larger decimation, and taps / decimation
+    swapped on a live object through its public attributes (the handle is refreshed, no new object needed)."""
+    from numpy import genfromtxt
+
+    n = 200_000
+    x = synth.digitiser_stream(n, 9).astype(np.float32)
+    ddc = _ddc(taps_dir, 16)
+    y16 = ddc.run(x, 100e6)
+    ddc.ddc_filter_coeffs = genfromtxt(os.path.join(taps_dir, "ddc_coeff_53MHz.csv"), delimiter=",")
+    ddc.decimation_factor = 32
+    y32 = ddc.run(x, 53.5e6)
+    for y, d, fc, csv in ((y16, 16, 100e6, "ddc_coeff_107MHz.csv"), (y32, 32, 53.5e6, "ddc_coeff_53MHz.csv")):
+        tp = genfromtxt(os.path.join(taps_dir, csv), delimiter=",")
+        emax, el2 = rel_err(y, orc.ddc_reference(x, fc, tp, d, FS))
+        assert emax <= TOL_MAX and el2 <= TOL_L2, (d, emax, el2)
