@@ -369,6 +369,258 @@ ddc_fused_w_kernel(const __grid_constant__ RunParams p, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Small decimations (D = 4, 8) on the same machinery: output m = NQ m' + q (NQ = 16 / D) is
+//      y[NQ m' + q] = sum_k c[k] x[16 m' + D q + k] = sum_k' c_q[k'] x[16 m' + k'],      c_q[k'] = c[k' - D q],
+// i.e. NQ interleaved decimate-by-16 filters with SHIFTED tap sets over the SAME staged chunk (T' = T + D (NQ - 1) taps
+// each, the same total flops as the direct D-decimating form).  A warp runs the fast FIR NQ times over its chunk, once per
+// tap set, and stores run q's outputs at stride NQ.  The tap count is 16 NJG + JL blocks: NJG groups of 16 blocks and a
+// last group of JL (even, <= 18) blocks, so that T' = 264 costs 18 blocks, not 32.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int JT, int NQ>
+struct WQCfg : PCfg<16, JT, 1> {
+    using B = PCfg<16, JT, 1>;
+    static_assert(JT % 2 == 0, "even number of tap blocks");
+    // tap groups: NJG groups of 16 blocks, then a last group of JL blocks.  A remainder of 2 blocks is merged into the last
+    // group (JL = 18): a 2-block pass would load 9 window entries for 48 FFMA2 and run at a quarter of the FMA rate.
+    static constexpr int JL = JT <= 18 ? JT : (JT % 16 == 0 ? 16 : (JT % 16 == 2 ? 18 : JT % 16));
+    static constexpr int NJG = (JT - JL) / 16;
+    static constexpr int JPA = NJG > 0 ? 16 : JL;  // blocks of the first pass
+    static constexpr int RH = B::R / 2;
+    static constexpr int TQ4 = 3 * (JT / 2) * 8;   // float4 per tap set (3 (JT/2) 16 complex)
+    static constexpr int NTW = NQ * 3 * (JT / 2) * 16;
+    static constexpr int WROWS_MAX = 4;            // thread-rows a pass window can span (R + 18 - 1 = 25 blocks)
+};
+
+template <int R>
+__device__ __forceinline__ void wq_epilogue(const float2 (&y)[R], const float2 (&rot_thr)[R], unsigned long long chunk_phase,
+                                            float2* o, int stride, int left) {
+    const float2 rot_chunk = nco_rot_bf(chunk_phase);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float2 z = cmul(cmul(y[r], rot_thr[r]), rot_chunk);
+        st_cs_v2_if(o + (long long)r * stride, z.x, z.y, r < left);
+    }
+}
+
+template <int JT, int NQ>
+__global__ void __launch_bounds__(WQCfg<JT, NQ>::NWARPS * 32 + 32 * WQCfg<JT, NQ>::NPROD, 1)
+ddc_fused_wq_kernel(const __grid_constant__ RunParams p, const __grid_constant__ TapsParam<WQCfg<JT, NQ>::NTW> taps) {
+    using C = WQCfg<JT, NQ>;
+    constexpr int D = 16;   // data geometry: 16-sample blocks, whatever the true decimation
+    constexpr int ROW = C::ROW, R = C::R, NWARPS = C::NWARPS, NG = C::NGROUPS;
+    constexpr int NSLOT = C::NSLOT, RH = C::RH, NJG = C::NJG, JL = C::JL, JPA = C::JPA;
+    constexpr int WANT = C::TOT_ROWS * ROW;
+    constexpr int NWA = R + JPA - 1;   // first-pass window
+    static_assert(R == 8 && C::V == 4, "geometry");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* empty_bar = full_bar + 16;
+    volatile int* slot_seq = reinterpret_cast<volatile int*>(smem_raw + 384);
+    float* buf = reinterpret_cast<float*>(smem_raw + C::HDR_BYTES);
+
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int lane = tid & 31;
+    if (tid == 0) {
+#pragma unroll 1
+        for (int s = 0; s < NSLOT; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+            slot_seq[s] = -1;
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int cps = (int)p.tiles_per_stream;
+    const int n_k = (int)((p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    const unsigned long long chunk_dph = (unsigned long long)((long long)C::CHUNK_OUT * D) * p.step_fx;
+
+    if (warp >= NWARPS) {
+        // ------------------------------------------------------------------ producer warps (as in ddc_fused_w_kernel)
+        constexpr int NP = C::NPROD;
+        const int pid = warp - NWARPS;
+        const long long pstride = (long long)NP * gridDim.x;
+        const int gs = (int)(pstride / cps), gc = (int)(pstride % cps);
+        const long long pfirst = blockIdx.x + (long long)pid * gridDim.x;
+        int cs = (int)(pfirst / cps), cc = (int)(pfirst % cps);
+        const int sbase = C::sub_base(pid), scnt = C::sub_count(pid);
+        int sidx = 0;
+        uint32_t par = 1;
+        for (int k = pid; k < n_k; k += NP) {
+            const int slot = sbase + sidx;
+            const bool leader = elect_one();
+            if (leader) {
+                mbar_wait(&empty_bar[slot], par);
+                slot_seq[slot] = k;
+            }
+            __syncwarp();
+            const float* src = reinterpret_cast<const float*>(p.in) + (long long)cs * p.in_stride + (long long)cc * C::CHUNK_S;
+            float* dst = buf + (size_t)slot * C::SLOT_FLOATS;
+            const long long valid = p.n_samples - (long long)cc * C::CHUNK_S;
+            if (valid >= WANT) {
+                if (leader) {
+                    mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)WANT * 4u);
+#pragma unroll
+                    for (int sr = 0; sr < C::NSR; ++sr) {
+                        constexpr int SR4 = C::SROWS;
+                        const int nrow = (C::TOT_ROWS - sr * SR4) < SR4 ? (C::TOT_ROWS - sr * SR4) : SR4;
+                        bulk_g2s(dst + sr * C::SRP, src + sr * SR4 * ROW, (uint32_t)nrow * ROW * 4u, &full_bar[slot]);
+                    }
+                }
+            } else {
+                uint32_t tx = 0;
+                for (int sr = 0; sr < C::NSR; ++sr) {
+                    const int cap = ((C::TOT_ROWS - sr * C::SROWS) < C::SROWS ? (C::TOT_ROWS - sr * C::SROWS) : C::SROWS) * ROW;
+                    const long long s0 = (long long)sr * C::SROWS * ROW;
+                    long long cnt = valid - s0;
+                    cnt = cnt < 0 ? 0 : (cnt > cap ? cap : cnt);
+                    const int bulk = (int)cnt & ~3;
+                    for (int e = bulk + lane; e < cap; e += 32) dst[sr * C::SRP + e] = (e < (int)cnt) ? src[s0 + e] : 0.f;
+                    tx += (uint32_t)bulk * 4u;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&full_bar[slot], tx);
+                    for (int sr = 0; sr < C::NSR; ++sr) {
+                        const int cap = ((C::TOT_ROWS - sr * C::SROWS) < C::SROWS ? (C::TOT_ROWS - sr * C::SROWS) : C::SROWS) * ROW;
+                        const long long s0 = (long long)sr * C::SROWS * ROW;
+                        long long cnt = valid - s0;
+                        cnt = cnt < 0 ? 0 : (cnt > cap ? cap : cnt);
+                        const int bulk = (int)cnt & ~3;
+                        if (bulk > 0) bulk_g2s(dst + sr * C::SRP, src + s0, (uint32_t)bulk * 4u, &full_bar[slot]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (++sidx == scnt) { sidx = 0; par ^= 1u; }
+            cs += gs;
+            cc += gc;
+            if (cc >= cps) { cc -= cps; ++cs; }
+        }
+    } else {
+        // ------------------------------------------------------------------ compute warps
+        const int grp = warp;
+        const int g = (lane & 7) * C::SROWS + (lane >> 3);
+        int rowoff[C::WROWS_MAX];
+#pragma unroll
+        for (int h = 0; h < C::WROWS_MAX; ++h) rowoff[h] = C::row_offset(g + h);
+        float2 rot_thr[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) rot_thr[r] = nco_rot((unsigned long long)((long long)(g * R + r) * D) * p.step_fx);
+
+        const long long kstride = (long long)NG * gridDim.x;
+        const int gs = (int)(kstride / cps), gc = (int)(kstride % cps);
+        const long long first = blockIdx.x + (long long)grp * gridDim.x;
+        int cs = (int)(first / cps), cc = (int)(first % cps);
+        const int sbase = C::sub_base(grp % C::NPROD), scnt = C::sub_count(grp % C::NPROD);
+        int sidx = (grp / C::NPROD) % scnt;
+        uint32_t par = (uint32_t)((grp / C::NPROD) / scnt) & 1u;
+
+        // deferred epilogue state: the previous run's sums and where they go
+        float2 yprev[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) yprev[r] = make_float2(0.f, 0.f);
+        float2* prev_o = p.out;
+        int prev_cc = 0, prev_left = 0;   // left = 0 disables the stores
+
+        float2 m0a[RH], m1a[RH], m2a[RH];
+        for (int k = grp; k < n_k; k += NG) {
+            const int slot = sbase + sidx;
+            while (slot_seq[slot] != k) {}
+            mbar_wait(&full_bar[slot], par);
+            const float* sbuf = buf + (size_t)slot * C::SLOT_FLOATS;
+            const float4* tq = &taps.c2[0];
+#pragma unroll 1
+            for (int q = 0; q < NQ; ++q, tq += C::TQ4) {
+#pragma unroll
+                for (int r = 0; r < RH; ++r) m0a[r] = m1a[r] = m2a[r] = make_float2(0.f, 0.f);
+                int xoff = 0;
+                const float4* tp = tq;
+                {   // first pass (tap group 0, phase group 0) with the previous run's epilogue in its basic block
+                    float4 w[NWA];
+#pragma unroll
+                    for (int b = 0; b < NWA; ++b)
+                        w[b] = *reinterpret_cast<const float4*>(sbuf + rowoff[b / R] + (b % R) * D);
+                    wq_epilogue<R>(yprev, rot_thr, p.phase0_fx + (unsigned long long)prev_cc * chunk_dph, prev_o, NQ, prev_left);
+                    w_fir_pg<D, JPA, R>(w, tp, m0a, m1a, m2a);
+                    xoff = 4;
+                    tp += 2;
+                }
+                int grow = g;   // first thread-row of the current pass window
+                if constexpr (NJG > 0) {
+                    int pgi = 1;
+#pragma unroll 1
+                    for (int pass = 1; pass < NJG * C::V; ++pass) {
+                        asm volatile("" : "+r"(xoff), "+r"(grow));
+                        int ro[C::WROWS_MAX];
+#pragma unroll
+                        for (int h = 0; h < C::WROWS_MAX; ++h) ro[h] = ((grow + h) / C::SROWS) * C::SRP + ((grow + h) % C::SROWS) * ROW;
+                        float4 w[R + 15];
+#pragma unroll
+                        for (int b = 0; b < R + 15; ++b)
+                            w[b] = *reinterpret_cast<const float4*>(sbuf + xoff + ro[b / R] + (b % R) * D);
+                        w_fir_pg<D, 16, R>(w, tp, m0a, m1a, m2a);
+                        ++pgi;
+                        xoff += 4;
+                        tp += 2;
+                        if (pgi == C::V) {
+                            pgi = 0;
+                            xoff = 0;
+                            grow += 16 / R;
+                            tp += 3 * 8 * (D / 2) - 2 * C::V;
+                        }
+                    }
+                    // after the last full group the loop leaves tp / grow / xoff at (group NJG, phase group 0)
+                }
+                {
+                    // last tap group: JL blocks starting at block 16 NJG; phase groups 0 .. 3 (1 .. 3 when it was also the
+                    // first pass)
+                    constexpr int NWL = R + JL - 1;
+                    constexpr int WROWS_L = (NWL - 1) / R + 1;
+#pragma unroll 1
+                    for (int pg = (NJG > 0 ? 0 : 1); pg < C::V; ++pg, tp += 2) {
+                        asm volatile("" : "+r"(xoff), "+r"(grow));
+                        int ro[WROWS_L];
+#pragma unroll
+                        for (int h = 0; h < WROWS_L; ++h) ro[h] = ((grow + h) / C::SROWS) * C::SRP + ((grow + h) % C::SROWS) * ROW;
+                        float4 w[NWL];
+#pragma unroll
+                        for (int b = 0; b < NWL; ++b)
+                            w[b] = *reinterpret_cast<const float4*>(sbuf + xoff + ro[b / R] + (b % R) * D);
+                        w_fir_pg<D, JL, R>(w, tp, m0a, m1a, m2a);
+                        xoff += 4;
+                    }
+                }
+                // the chunk goes back to the producer after the last tap set
+                __syncwarp();
+                mbar_arrive_if(&empty_bar[slot], lane == 0 && q == NQ - 1);
+
+#pragma unroll
+                for (int r = 0; r < RH; ++r) {
+                    yprev[2 * r] = make_float2(m0a[r].x + m1a[r].x, m0a[r].y + m1a[r].y);
+                    yprev[2 * r + 1] = make_float2(m1a[r].x - m2a[r].x, m1a[r].y - m2a[r].y);
+                }
+                // outputs of this run: m = NQ m' + q for m' = m0 .. m0 + R - 1; those with m < n_out exist
+                const long long m0 = (long long)cc * C::CHUNK_OUT + g * R;
+                const long long nq = (p.n_out - q + NQ - 1) / NQ;
+                const long long lf = nq - m0;
+                prev_left = (int)(lf < 0 ? 0 : (lf > R ? R : lf));
+                prev_cc = cc;
+                prev_o = p.out + (long long)cs * p.out_stride + m0 * NQ + q;
+            }
+            sidx += NG / C::NPROD;
+            if (sidx >= scnt) { sidx -= scnt; par ^= 1u; }
+            cs += gs;
+            cc += gc;
+            if (cc >= cps) { cc -= cps; ++cs; }
+        }
+        wq_epilogue<R>(yprev, rot_thr, p.phase0_fx + (unsigned long long)prev_cc * chunk_dph, prev_o, NQ, prev_left);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // packed 10-bit input (BASELINE configs[2]; reference stub ddc.py:68-83): raw TMA ring + in-warp unpack as in
 // ddc_fused_p10_kernel, with the fast FIR and the deferred branch-free epilogue.  The unpack avoids I2F (quarter-rate
 // conversion pipe): the 10 bits are placed in the mantissa of 2^23 with the sign bit flipped,

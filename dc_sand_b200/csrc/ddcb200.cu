@@ -89,6 +89,9 @@ struct ddcb200 {
     std::vector<float2> wt_cache;
     double wt_step = 0.0;
     int wt_jt = 0, wt_d = 0;
+    std::vector<float2> wq_cache;   // same for the small-decimation kernel
+    double wq_step = 0.0;
+    int wq_jt = 0, wq_nq = 0;
 };
 
 namespace {
@@ -134,6 +137,35 @@ void make_wtaps(const ddcb200* h, double step, int jt, int D, float2* out) {
             out[(3 * i + 1) * D + d] = make_float2((float)(er + orr), (float)(ei + oi));
             out[(3 * i + 2) * D + d] = make_float2((float)orr, (float)oi);
         }
+}
+
+// Kernel WQ (small decimations, ddc_kernel_w.cuh): NQ = 16 / D shifted tap sets c_q[k'] = c[k' - D q] (same phase law in k'),
+// each laid out like kernel W's: index q * 3 (jt/2) 16 + (3 i + seq) 16 + d.
+void make_wqtaps(const ddcb200* h, double step, int jt, int nq, int D, float2* out) {
+    const int T = (int)h->taps.size();
+    const double fstep = step - std::floor(step);
+    for (int q = 0; q < nq; ++q) {
+        auto c = [&](int kp, double& re, double& im) {
+            const int k = kp - D * q;
+            if (k < 0 || k >= T) { re = im = 0.0; return; }
+            const double hk = h->taps[T - 1 - k] / h->taps_sum;
+            double ph = fstep * (double)kp;
+            ph -= std::floor(ph);
+            const double a = -2.0 * M_PI * ph;
+            re = hk * std::cos(a);
+            im = hk * std::sin(a);
+        };
+        float2* o = out + (size_t)q * 3 * (jt / 2) * 16;
+        for (int i = 0; i < jt / 2; ++i)
+            for (int d = 0; d < 16; ++d) {
+                double er, ei, orr, oi;
+                c(2 * i * 16 + d, er, ei);
+                c((2 * i + 1) * 16 + d, orr, oi);
+                o[(3 * i + 0) * 16 + d] = make_float2((float)er, (float)ei);
+                o[(3 * i + 1) * 16 + d] = make_float2((float)(er + orr), (float)(ei + oi));
+                o[(3 * i + 2) * 16 + d] = make_float2((float)orr, (float)oi);
+            }
+    }
 }
 
 // cached front end of make_wtaps (invalidated by set_taps / set_decimation through wt_jt = 0)
@@ -376,6 +408,47 @@ int launch_w10_j(ddcb200* h, RunParams& p, cudaStream_t st, double step, int jt)
     }
 }
 
+template <int JT, int NQ>
+int launch_wq(ddcb200* h, RunParams& p, cudaStream_t st, double step) {
+    using C = WQCfg<JT, NQ>;
+    auto kern = ddc_fused_wq_kernel<JT, NQ>;
+    const size_t smem = C::HDR_BYTES + (size_t)C::NSLOT * C::SLOT_FLOATS * sizeof(float);
+    static bool attr_set[64] = {};
+    if (h->device < 64 && !attr_set[h->device]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[h->device] = true;
+    }
+    static_assert(sizeof(TapsParam<C::NTW>) + sizeof(RunParams) <= 32764, "kernel parameter space");
+    TapsParam<C::NTW> tp;
+    if (h->wq_jt != JT || h->wq_nq != NQ || h->wq_step != step || h->wq_cache.size() != (size_t)C::NTW) {
+        h->wq_cache.resize((size_t)C::NTW);
+        make_wqtaps(h, step, JT, NQ, 16 / NQ, h->wq_cache.data());
+        h->wq_jt = JT;
+        h->wq_nq = NQ;
+        h->wq_step = step;
+    }
+    std::memcpy(tp.c2, h->wq_cache.data(), sizeof(float2) * (size_t)C::NTW);
+    const long long grid = std::min<long long>(p.total_tiles, h->sm_count);
+    kern<<<(unsigned)grid, C::NWARPS * 32 + 32 * C::NPROD, smem, st>>>(p, tp);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    char name[96];
+    snprintf(name, sizeof(name), "fused_fast_fir_subfilters<D%d,NQ%d,J%d,SLOTS%d>", 16 / NQ, NQ, JT, C::NSLOT);
+    h->last_variant = name;
+    return DDCB200_OK;
+}
+
+// The small-decimation kernel is only instantiated where it was measured faster than the rotating-window tile kernel:
+// D = 8 with 513 .. 1048 taps (66 tap blocks), 0.495 against 0.545 ms at T = 1024, N = 2^26.  With fewer tap blocks the
+// tile kernel's 82-94 % FMA-pipe utilisation beats the 7 % net flop saving (profiles/r1_sweep_taps_decimation.md).
+template <int NQ>
+int launch_wq_j(ddcb200* h, RunParams& p, cudaStream_t st, double step, int jt) {
+    if constexpr (NQ == 2) {
+        if (jt == 66) return launch_wq<66, NQ>(h, p, st, step);
+    }
+    return fail(DDCB200_EINVAL, "small-decimation kernel: unsupported tap-block count %d", jt);
+}
+
 template <int D>
 int launch_p_j(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, int jt, int ks) {
     if (ks == 2) {
@@ -475,6 +548,23 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
             case 16: return launch_p10_j<16>(h, p, ctp.data(), st, jt);
             case 32: return launch_p10_j<32>(h, p, ctp.data(), st, jt);
             default: return launch_p10_j<64>(h, p, ctp.data(), st, jt);
+        }
+    }
+
+    // ---- small decimations (D = 4, 8): NQ = 16 / D interleaved decimate-by-16 fast FIRs with shifted tap sets --------------
+    if (aligned_f32(d_in, in_stride, packed) && (D == 4 || D == 8) && (h->force_variant == 0 || h->force_variant == 7)) {
+        const int nq = 16 / D;
+        const int Tq = T + D * (nq - 1);
+        const int jneed = (Tq + 15) / 16;
+        const int jt = (nq == 2 && jneed > 34 && jneed <= 66) ? 66 : 0;   // see launch_wq_j
+        if (jt) {
+            const long long mq = (M + nq - 1) / nq;           // decimate-by-16 outputs per tap set
+            p.tiles_per_stream = (mq + 255) / 256;
+            p.total_tiles = p.tiles_per_stream * n_streams;
+            p.n_taps = jt * 16;
+            p.n_tap_blocks = jt;
+            p.m_begin = 0;
+            return nq == 2 ? launch_wq_j<2>(h, p, st, step, jt) : launch_wq_j<4>(h, p, st, step, jt);
         }
     }
 
@@ -669,7 +759,8 @@ int ddcb200_set_taps(ddcb200_t* h, const double* taps, int n_taps) {
     if (!(s != 0.0) || !std::isfinite(s)) return fail(DDCB200_EINVAL, "set_taps: sum of taps is %g", s);
     h->taps.assign(taps, taps + n_taps);
     h->taps_sum = s;
-    h->wt_jt = 0;   // invalidate the folded-tap cache
+    h->wt_jt = 0;   // invalidate the folded-tap caches
+    h->wq_jt = 0;
     return DDCB200_OK;
 }
 
