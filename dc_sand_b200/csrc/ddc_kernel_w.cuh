@@ -39,7 +39,8 @@ struct WCfg : PCfg<D, JT, 1> {
     static constexpr int NS = RH + JH - 1;         // entries of each derived sequence a thread touches per pass
     static constexpr int NWP = B::R + JP - 1;      // blocks of the register window of one pass
     static constexpr int WROWS = (NWP - 1) / B::R + 1;   // thread-rows a pass window spans
-    static constexpr int NTW = 3 * (JT / 2) * D;   // complex taps passed to the kernel
+    static constexpr int NTW = 3 * (JT / 2) * D;   // complex taps passed to the kernel (one level)
+    static constexpr int NTW2 = 9 * ((JT + 3) / 4) * D;   // two nested levels
 };
 
 #ifndef DDCB200_W10_UNPACK_UNROLL
@@ -113,6 +114,78 @@ __device__ __forceinline__ void w_fir_pg(const float4 (&w)[R + JT - 1], const fl
     }
 }
 
+// Two nested levels of the 2-by-2 fast FIR (9/16 of the multiplies): each of the three half-rate FIRs of w_fir_pg
+// (sequence s_a, taps g_a) is split once more into three quarter-rate FIRs
+//      A_ab[rho] = sum_iota t_ab[rho + iota] * h_ab[iota],       rho = 0 .. R/4-1,  iota = 0 .. JP/4-1,
+//      t_a0[v] = s_a[2v] - s_a[2v+1],  t_a1[v] = s_a[2v+1],  t_a2[v] = s_a[2v+1] - s_a[2v+2]          (data, in registers)
+//      h_a0[i] = g_a[2i],              h_a1[i] = g_a[2i] + g_a[2i+1],   h_a2[i] = g_a[2i+1]            (taps, from the host)
+// and M_a[2 rho] = A_a0 + A_a1, M_a[2 rho + 1] = A_a1 - A_a2 once per chunk.  Per phase group: 9 (R/4)(JP/4) 4 = 288 FFMA2
+// and 104 FADD2 at R = 8, JP = 16, against 384 + 44 for one level and 512 for the direct form.  Rounding error of the
+// nested form on the reference filter: 3.0e-7 of max|y| (tools/winograd_error.py), below the one-level and direct forms.
+// Tap index: ((9 iota + 3 a + b) D + d).
+// MEASURED: slower than one level at R = 8 (0.252 against 0.229 ms compute-only, T = 256, 2^28 samples): every tap fetch
+// (LDCU.64) feeds only R / 4 = 2 FFMA2 and the uniform datapath becomes the limit.  It would need R = 16 outputs per thread,
+// i.e. 32 KB chunks that do not fit an 8-warp ring.  Kept behind option "variant" = 9 for that experiment only.
+template <int D, int JP, int R>
+__device__ __forceinline__ void w2_fir_pg(const float4 (&w)[R + JP - 1], const float4* tp, float2 (&acc)[9][R / 4]) {
+    static_assert(JP % 4 == 0 && R % 4 == 0, "nested fast FIR needs multiples of four");
+    constexpr int JQ = JP / 4, RQ = R / 4;
+    constexpr int NS1 = R / 2 + JP / 2 - 1;     // level-1 sequence length
+    constexpr int NS2 = RQ + JQ - 1;            // level-2 sequence length
+    float4 t[9][NS2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float4 s[NS1];
+#pragma unroll
+        for (int n = 0; n < NS1; ++n)
+            s[n] = a == 0 ? sub4(w[2 * n], w[2 * n + 1]) : (a == 1 ? w[2 * n + 1] : sub4(w[2 * n + 1], w[2 * n + 2]));
+#pragma unroll
+        for (int v = 0; v < NS2; ++v) {
+            t[3 * a + 0][v] = sub4(s[2 * v], s[2 * v + 1]);
+            t[3 * a + 1][v] = s[2 * v + 1];
+            t[3 * a + 2][v] = sub4(s[2 * v + 1], s[2 * v + 2]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < JQ; ++i) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float4 tt[9];
+#pragma unroll
+            for (int ab = 0; ab < 9; ++ab) tt[ab] = tp[(9 * i + ab) * (D / 2) + half];
+#pragma unroll
+            for (int ab = 0; ab < 9; ++ab)
+#pragma unroll
+                for (int r = 0; r < RQ; ++r)
+                    acc[ab][r] = ffma2(half ? t[ab][r + i].z : t[ab][r + i].x, make_float2(tt[ab].x, tt[ab].y), acc[ab][r]);
+#pragma unroll
+            for (int ab = 0; ab < 9; ++ab)
+#pragma unroll
+                for (int r = 0; r < RQ; ++r)
+                    acc[ab][r] = ffma2(half ? t[ab][r + i].w : t[ab][r + i].y, make_float2(tt[ab].z, tt[ab].w), acc[ab][r]);
+        }
+    }
+}
+
+// y[0 .. R-1] from the nine quarter-rate sums
+template <int R>
+__device__ __forceinline__ void w2_combine(const float2 (&acc)[9][R / 4], float2 (&y)[R]) {
+    constexpr int RQ = R / 4;
+    float2 m[3][2 * RQ];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int r = 0; r < RQ; ++r) {
+            m[a][2 * r] = make_float2(acc[3 * a][r].x + acc[3 * a + 1][r].x, acc[3 * a][r].y + acc[3 * a + 1][r].y);
+            m[a][2 * r + 1] = make_float2(acc[3 * a + 1][r].x - acc[3 * a + 2][r].x, acc[3 * a + 1][r].y - acc[3 * a + 2][r].y);
+        }
+#pragma unroll
+    for (int r = 0; r < 2 * RQ; ++r) {
+        y[2 * r] = make_float2(m[0][r].x + m[1][r].x, m[0][r].y + m[1][r].y);
+        y[2 * r + 1] = make_float2(m[1][r].x - m[2][r].x, m[1][r].y - m[2][r].y);
+    }
+}
+
 // Branch-free epilogue (so that it can live inside the FIR's basic block, deferred by one chunk): polynomial NCO and
 // predicated stores.  A thread's R outputs start at a multiple of R elements of its output row; the row itself may start
 // on an odd complex64 element ([streams, M] arrays with odd M), so the 16-byte pairing is chosen per thread from the
@@ -142,9 +215,11 @@ __device__ __forceinline__ void w_epilogue(const float2 (&y)[R], const float2 (&
 // ---------------------------------------------------------------------------------------------------------------------
 // float32 input
 // ---------------------------------------------------------------------------------------------------------------------
-template <int D, int JT>
+// NEST = 0: one fast-FIR level (w_fir_pg, 3 (JT/2) D complex taps); NEST = 1: two nested levels (w2_fir_pg, 9 (JT/4) D taps)
+template <int D, int JT, int NEST>
 __global__ void __launch_bounds__(WCfg<D, JT>::NWARPS * 32 + 32 * WCfg<D, JT>::NPROD, 1)
-ddc_fused_w_kernel(const __grid_constant__ RunParams p, const __grid_constant__ TapsParam<WCfg<D, JT>::NTW> taps) {
+ddc_fused_w_kernel(const __grid_constant__ RunParams p,
+                   const __grid_constant__ TapsParam<(NEST ? WCfg<D, JT>::NTW2 : WCfg<D, JT>::NTW)> taps) {
     using C = WCfg<D, JT>;
     constexpr int ROW = C::ROW, R = C::R, NW = C::NWP, NWARPS = C::NWARPS, NG = C::NGROUPS;
     constexpr int NSLOT = C::NSLOT, RH = C::RH, NS = C::NS, JP = C::JP, NJG = C::NJG;
@@ -266,7 +341,14 @@ ddc_fused_w_kernel(const __grid_constant__ RunParams p, const __grid_constant__ 
         int prev_cc = 0;
         long long prev_nout = 0;   // 0 disables the stores
 
-        float2 m0a[RH], m1a[RH], m2a[RH];
+        float2 m0a[RH], m1a[RH], m2a[RH];   // NEST = 0
+        constexpr int RQN = NEST ? R / 4 : 1;
+        float2 acc9[9][RQN];                // NEST = 1
+        constexpr int TPG = NEST ? 9 * (JP / 4) * (D / 2) : 3 * (JP / 2) * (D / 2);   // float4 per tap group of JP blocks
+        auto fir = [&](const float4(&w)[NW], const float4* tpp) {
+            if constexpr (NEST) w2_fir_pg<D, JP, R>(w, tpp, acc9);
+            else w_fir_pg<D, JP, R>(w, tpp, m0a, m1a, m2a);
+        };
         long long t_wait = 0;
         const long long t_begin = clock64();
         const bool memonly = (p.debug_mode & 255) == 2;   // tuning aid: ring traffic without the FIR
@@ -281,6 +363,10 @@ ddc_fused_w_kernel(const __grid_constant__ RunParams p, const __grid_constant__ 
             const float* sbuf = buf + (size_t)slot * C::SLOT_FLOATS;
 #pragma unroll
             for (int r = 0; r < RH; ++r) m0a[r] = m1a[r] = m2a[r] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int ab = 0; ab < 9; ++ab)
+#pragma unroll
+                for (int r = 0; r < RQN; ++r) acc9[ab][r] = make_float2(0.f, 0.f);
 
             if (memonly) {
                 if (sbuf[rowoff[0]] == 123.456f) m0a[0].x = 1.f;
@@ -296,7 +382,7 @@ ddc_fused_w_kernel(const __grid_constant__ RunParams p, const __grid_constant__ 
                     for (int b = 0; b < NW; ++b)
                         w[b] = *reinterpret_cast<const float4*>(sbuf + rowoff[b / R] + (b % R) * D);
                     w_epilogue<R>(yprev, rot_thr, p.phase0_fx + (unsigned long long)prev_cc * chunk_dph, prev_m0, prev_o, prev_nout);
-                    w_fir_pg<D, JP, R>(w, tp, m0a, m1a, m2a);
+                    fir(w, tp);
                     xoff = 4;
                     tp += 2;
                 }
@@ -309,7 +395,7 @@ ddc_fused_w_kernel(const __grid_constant__ RunParams p, const __grid_constant__ 
                         for (int b = 0; b < NW; ++b)
                             w[b] = *reinterpret_cast<const float4*>(sbuf + xoff + rowoff[b / R] + (b % R) * D);
                         xoff += 4;
-                        w_fir_pg<D, JP, R>(w, tp, m0a, m1a, m2a);
+                        fir(w, tp);
                     }
                 } else {
                     // passes 1 .. NJG V - 1 share one loop body: pass = jg V + pg; the per-thread row offsets of tap group jg
@@ -326,7 +412,7 @@ ddc_fused_w_kernel(const __grid_constant__ RunParams p, const __grid_constant__ 
 #pragma unroll
                         for (int b = 0; b < NW; ++b)
                             w[b] = *reinterpret_cast<const float4*>(sbuf + xoff + ro[b / R] + (b % R) * D);
-                        w_fir_pg<D, JP, R>(w, tp, m0a, m1a, m2a);
+                        fir(w, tp);
                         // next pass: next phase group, or phase group 0 of the next tap group
                         ++pgi;
                         xoff += 4;
@@ -335,7 +421,7 @@ ddc_fused_w_kernel(const __grid_constant__ RunParams p, const __grid_constant__ 
                             pgi = 0;
                             xoff = 0;
                             grow += JP / R;
-                            tp += 3 * (JP / 2) * (D / 2) - 2 * C::V;   // tap set (i = JP/2 (jg+1), seq 0), phase group 0
+                            tp += TPG - 2 * C::V;   // first tap set of the next group, phase group 0
                         }
                     }
                 }
@@ -344,10 +430,14 @@ ddc_fused_w_kernel(const __grid_constant__ RunParams p, const __grid_constant__ 
             if (lane == 0 && (p.debug_mode & 255) != 1) mbar_arrive(&empty_bar[slot]);
 
             // combine the three half-rate sums and hand them to the next iteration's deferred epilogue
+            if constexpr (NEST) {
+                w2_combine<R>(acc9, yprev);
+            } else {
 #pragma unroll
-            for (int r = 0; r < RH; ++r) {
-                yprev[2 * r] = make_float2(m0a[r].x + m1a[r].x, m0a[r].y + m1a[r].y);
-                yprev[2 * r + 1] = make_float2(m1a[r].x - m2a[r].x, m1a[r].y - m2a[r].y);
+                for (int r = 0; r < RH; ++r) {
+                    yprev[2 * r] = make_float2(m0a[r].x + m1a[r].x, m0a[r].y + m1a[r].y);
+                    yprev[2 * r + 1] = make_float2(m1a[r].x - m2a[r].x, m1a[r].y - m2a[r].y);
+                }
             }
             prev_cc = cc;
             prev_m0 = (long long)cc * C::CHUNK_OUT + g * R;

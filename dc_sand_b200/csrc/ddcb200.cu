@@ -88,7 +88,7 @@ struct ddcb200 {
     // folded fast-FIR taps of the last (step, jt, D): streaming callers repeat the same step call after call
     std::vector<float2> wt_cache;
     double wt_step = 0.0;
-    int wt_jt = 0, wt_d = 0;
+    int wt_jt = 0, wt_d = 0, wt_nest = 0;
     std::vector<float2> wq_cache;   // same for the small-decimation kernel
     double wq_step = 0.0;
     int wq_jt = 0, wq_nq = 0;
@@ -168,9 +168,44 @@ void make_wqtaps(const ddcb200* h, double step, int jt, int nq, int D, float2* o
     }
 }
 
+// Nested fast FIR (w2_fir_pg): for tap quad iota and phase d the nine tap sets (a, b) at index ((9 iota + 3 a + b) D + d):
+//   g_0[i] = c[2i], g_1[i] = c[2i] + c[2i+1], g_2[i] = c[2i+1];   h_a0 = g_a[2 iota], h_a1 = g_a[2 iota] + g_a[2 iota + 1], h_a2 = g_a[2 iota + 1]
+void make_w2taps(const ddcb200* h, double step, int jt, int D, float2* out) {
+    const int T = (int)h->taps.size();
+    const double fstep = step - std::floor(step);
+    auto c = [&](int k, double* v) {
+        v[0] = v[1] = 0.0;
+        if (k >= T) return;
+        const double hk = h->taps[T - 1 - k] / h->taps_sum;
+        double ph = fstep * (double)k;
+        ph -= std::floor(ph);
+        const double a = -2.0 * M_PI * ph;
+        v[0] = hk * std::cos(a);
+        v[1] = hk * std::sin(a);
+    };
+    for (int io = 0; io < jt / 4; ++io)
+        for (int d = 0; d < D; ++d) {
+            double cb[4][2], g[3][2][2];   // c of blocks 4 io .. 4 io + 3; g[a][i - 2 io]
+            for (int b = 0; b < 4; ++b) c((4 * io + b) * D + d, cb[b]);
+            for (int i = 0; i < 2; ++i)
+                for (int z = 0; z < 2; ++z) {
+                    g[0][i][z] = cb[2 * i][z];
+                    g[1][i][z] = cb[2 * i][z] + cb[2 * i + 1][z];
+                    g[2][i][z] = cb[2 * i + 1][z];
+                }
+            for (int a = 0; a < 3; ++a) {
+                float2* o = out + (size_t)(9 * io + 3 * a) * D + d;
+                o[0] = make_float2((float)g[a][0][0], (float)g[a][0][1]);
+                o[D] = make_float2((float)(g[a][0][0] + g[a][1][0]), (float)(g[a][0][1] + g[a][1][1]));
+                o[2 * D] = make_float2((float)g[a][1][0], (float)g[a][1][1]);
+            }
+        }
+}
+
 // cached front end of make_wtaps (invalidated by set_taps / set_decimation through wt_jt = 0)
 const float2* cached_wtaps(ddcb200* h, double step, int jt, int D) {
-    if (h->wt_jt != jt || h->wt_d != D || h->wt_step != step || h->wt_cache.size() != (size_t)(3 * (jt / 2) * D)) {
+    if (h->wt_jt != jt || h->wt_d != D || h->wt_nest != 0 || h->wt_step != step || h->wt_cache.size() != (size_t)(3 * (jt / 2) * D)) {
+        h->wt_nest = 0;
         h->wt_cache.resize((size_t)(3 * (jt / 2) * D));
         make_wtaps(h, step, jt, D, h->wt_cache.data());
         h->wt_step = step;
@@ -340,39 +375,55 @@ int launch_pd_j(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, int
     }
 }
 
-template <int D, int JT>
+template <int D, int JT, int NEST>
 int launch_w(ddcb200* h, RunParams& p, cudaStream_t st, double step) {
     using C = WCfg<D, JT>;
-    auto kern = ddc_fused_w_kernel<D, JT>;
+    constexpr int NT = NEST ? C::NTW2 : C::NTW;
+    auto kern = ddc_fused_w_kernel<D, JT, NEST>;
     const size_t smem = C::HDR_BYTES + (size_t)C::NSLOT * C::SLOT_FLOATS * sizeof(float);
     static bool attr_set[64] = {};
     if (h->device < 64 && !attr_set[h->device]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[h->device] = true;
     }
-    TapsParam<C::NTW> tp;
-    std::memcpy(tp.c2, cached_wtaps(h, step, JT, D), sizeof(float2) * (size_t)C::NTW);
+    TapsParam<NT> tp;
+    // folded taps of the last (step, jt, D, nesting): streaming callers repeat the same step call after call
+    if (h->wt_jt != JT || h->wt_d != D || h->wt_nest != NEST || h->wt_step != step || h->wt_cache.size() != (size_t)NT) {
+        h->wt_cache.assign((size_t)NT, make_float2(0.f, 0.f));
+        if (NEST) make_w2taps(h, step, JT, D, h->wt_cache.data());
+        else make_wtaps(h, step, JT, D, h->wt_cache.data());
+        h->wt_step = step;
+        h->wt_jt = JT;
+        h->wt_d = D;
+        h->wt_nest = NEST;
+    }
+    std::memcpy(tp.c2, h->wt_cache.data(), sizeof(float2) * (size_t)NT);
     const long long grid = std::min<long long>(p.total_tiles, h->sm_count);
     kern<<<(unsigned)grid, C::NWARPS * 32 + 32 * C::NPROD, smem, st>>>(p, tp);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
     char name[96];
-    snprintf(name, sizeof(name), "fused_fast_fir<D%d,R%d,J%d,SLOTS%d>", D, C::R, JT, C::NSLOT);
+    snprintf(name, sizeof(name), "fused_fast_fir%s<D%d,R%d,J%d,SLOTS%d>", NEST ? "_nested" : "", D, C::R, JT, C::NSLOT);
     h->last_variant = name;
     return DDCB200_OK;
 }
 
 template <int D>
-int launch_w_j(ddcb200* h, RunParams& p, cudaStream_t st, double step, int jt) {
+int launch_w_j(ddcb200* h, RunParams& p, cudaStream_t st, double step, int jt, bool nest) {
+    if constexpr (D == 16) {   // two nested levels need R = 8 outputs per thread
+        // Experimental (option "variant" 9): measured SLOWER than one level -- 0.252 against 0.229 ms compute-only at
+        // T = 256 -- because each tap fetch then feeds only two FFMA2 (R / 4 outputs); kept for one configuration only.
+        if (nest && jt == 16) return launch_w<D, 16, 1>(h, p, st, step);
+    }
     switch (jt) {
-        case 4: return launch_w<D, 4>(h, p, st, step);
-        case 8: return launch_w<D, 8>(h, p, st, step);
-        case 16: return launch_w<D, 16>(h, p, st, step);
+        case 4: return launch_w<D, 4, 0>(h, p, st, step);
+        case 8: return launch_w<D, 8, 0>(h, p, st, step);
+        case 16: return launch_w<D, 16, 0>(h, p, st, step);
         default: break;
     }
     if constexpr (D == 16) {   // long filters: passes of 16 tap blocks (T <= 1024)
-        if (jt == 32) return launch_w<D, 32>(h, p, st, step);
-        if (jt == 64) return launch_w<D, 64>(h, p, st, step);
+        if (jt == 32) return launch_w<D, 32, 0>(h, p, st, step);
+        if (jt == 64) return launch_w<D, 64, 0>(h, p, st, step);
     }
     return fail(DDCB200_EINVAL, "fast-FIR kernel: unsupported tap-block count %d at D = %d", jt, D);
 }
@@ -569,9 +620,10 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
     }
 
     // ---- kernel P (phase-major, R = 128/D outputs per thread): short polyphase branches, J = ceil(T/D) <= 16 ------
-    const bool long_w = D == 16 && (T + D - 1) / D > 16 && (T + D - 1) / D <= 64 && (h->force_variant == 0 || h->force_variant == 7);
+    const bool long_w = D == 16 && (T + D - 1) / D > 16 && (T + D - 1) / D <= 64 &&
+                        (h->force_variant == 0 || h->force_variant == 7 || h->force_variant == 9);
     if (aligned_f32(d_in, in_stride, packed) && (D == 16 || D == 32 || D == 64) && ((T + D - 1) / D <= 16 || long_w) &&
-        (h->force_variant == 0 || (h->force_variant >= 5 && h->force_variant <= 8))) {
+        (h->force_variant == 0 || (h->force_variant >= 5 && h->force_variant <= 9))) {
         const int ksp = (h->force_variant == 6) ? 2 : 1;   // option "variant": 5 (= auto) one warp per chunk, 6 = two (slower)
         const int Jp = (T + D - 1) / D;
         const int jt = Jp <= 4 ? 4 : (Jp <= 8 ? 8 : (Jp <= 16 ? 16 : (Jp <= 32 ? 32 : 64)));
@@ -583,12 +635,13 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         p.m_begin = 0;
         // option "variant": 0 auto; 5 / 6 kernel P with one / two warps per chunk; 7 fast FIR (kernel W); 8 deferred-epilogue P.
         // Auto picks the fast-FIR kernel where a thread has R = 8 outputs (D = 16) and the output rows allow 16-byte stores.
-        const bool want_w = h->force_variant == 7 || (h->force_variant == 0 && D == 16);
+        const bool want_w = h->force_variant == 7 || h->force_variant == 9 || (h->force_variant == 0 && D == 16);
         if (want_w) {   // any complex64-aligned output: the epilogue picks its 16-byte pairing per thread
+            const bool nest = h->force_variant == 9;   // option "variant" 9: two nested fast-FIR levels (D = 16)
             switch (D) {
-                case 16: return launch_w_j<16>(h, p, st, step, jt);
-                case 32: return launch_w_j<32>(h, p, st, step, jt);
-                default: return launch_w_j<64>(h, p, st, step, jt);
+                case 16: return launch_w_j<16>(h, p, st, step, jt, nest);
+                case 32: return launch_w_j<32>(h, p, st, step, jt, nest);
+                default: return launch_w_j<64>(h, p, st, step, jt, nest);
             }
         }
         std::vector<float2> ctp((size_t)jt * D);

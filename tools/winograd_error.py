@@ -90,3 +90,60 @@ if __name__ == "__main__":
     run(float_input=True)
     run(T=1024, D=16)
     run(T=512, D=32)
+
+
+def run_nested(T=256, D=16, n=1 << 18, fc=100e6, fs=1712e6, float_input=False):
+    """Two nested F(2,2) levels (9/16 of the multiplies): float32 emulation against the float64 oracle."""
+    tp = taps.coefficients("ddc_coeff_107MHz.csv") if T == 256 else __import__("scipy.signal").signal.firwin(T, 0.8 / D)
+    x = synth.digitiser_stream(n, 1234).astype(np.float32)
+    if float_input:
+        x = (x * np.float32(0.3713)).astype(np.float32)
+    step = orc.phase_step_cycles(n, fc, fs)
+    c, J = folded(tp, step, D)
+    J4 = -(-J // 4) * 4
+    cm = np.zeros((J4, D), np.complex128)
+    cm[:J] = c.reshape(J, D)
+    M = min(((n - T) // D + 1) // 4 * 4, 8192)
+    ref = orc.ddc_windowed_f64(x, 0, M, step, tp, D)
+    rot = np.exp(-2j * np.pi * ((np.arange(M) * D * step) % 1.0))
+    xb = np.zeros((M + J4 + 4) * D, np.float32)
+    xb[: min(len(x), len(xb))] = x[: len(xb)]
+    xb = xb.reshape(-1, D)
+    Q = M // 4
+    f32 = np.float32
+
+    def split_taps(g):      # g[i] -> (g[2i], g[2i]+g[2i+1], g[2i+1])
+        return g[0::2], g[0::2] + g[1::2], g[1::2]
+
+    def split_data(s):      # s[n] -> (s[2n]-s[2n+1], s[2n+1], s[2n+1]-s[2n+2]) in float32
+        L = (len(s) - 1) // 2
+        return (s[0:2 * L:2] - s[1:2 * L:2]).astype(f32), s[1:2 * L:2].astype(f32), (s[1:2 * L:2] - s[2:2 * L + 1:2]).astype(f32)
+
+    acc = np.zeros((3, 3, Q, 2), f32)
+    for d in range(D):
+        col = xb[:, d]
+        for a, (s1, g1) in enumerate(zip(split_data(col), split_taps(cm[:, d]))):
+            for b, (s2, g2) in enumerate(zip(split_data(s1), split_taps(g1))):
+                g2 = g2.astype(np.complex64)
+                for i in range(J4 // 4):
+                    seg = s2[i:i + Q]
+                    acc[a, b, :, 0] += seg * f32(g2[i].real)
+                    acc[a, b, :, 1] += seg * f32(g2[i].imag)
+    # level-2 combine: M_a[2p] = A + B, M_a[2p+1] = B - C
+    Ml = np.zeros((3, 2 * Q, 2), f32)
+    for a in range(3):
+        Ml[a, 0::2] = acc[a, 0] + acc[a, 1]
+        Ml[a, 1::2] = acc[a, 1] - acc[a, 2]
+    y = np.zeros((M, 2), f32)
+    y[0::2] = Ml[0] + Ml[1]
+    y[1::2] = Ml[1] - Ml[2]
+    yw = (y[:, 0].astype(np.float64) + 1j * y[:, 1]) * rot
+    s = np.abs(ref).max()
+    print(f"T={T} D={D} float_input={float_input} nested  max_err/max|ref| = {np.abs(yw - ref).max() / s:.3e}   "
+          f"rel_l2 = {np.linalg.norm(yw - ref) / np.linalg.norm(ref):.3e}")
+
+
+if __name__ == "__main__":
+    run_nested()
+    run_nested(float_input=True)
+    run_nested(T=1024, D=16)
