@@ -450,6 +450,27 @@ int launch_w10(ddcb200* h, RunParams& p, cudaStream_t st, double step) {
     return DDCB200_OK;
 }
 
+template <int D, int JT>
+int launch_w10s(ddcb200* h, RunParams& p, cudaStream_t st, double step) {
+    using C = W10SCfg<D, JT>;
+    auto kern = ddc_fused_w10s_kernel<D, JT>;
+    static bool attr_set[64] = {};
+    if (h->device < 64 && !attr_set[h->device]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        attr_set[h->device] = true;
+    }
+    TapsParam<C::NTW> tp;
+    std::memcpy(tp.c2, cached_wtaps(h, step, JT, D), sizeof(float2) * (size_t)C::NTW);
+    const long long grid = std::min<long long>(p.total_tiles, h->sm_count);
+    kern<<<(unsigned)grid, (C::NFIR + C::NUNP + 1) * 32, C::SMEM, st>>>(p, tp);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    char name[112];
+    snprintf(name, sizeof(name), "fused_fast_fir_packed10_split<D%d,R%d,J%d,RAW%d,FLOAT%d,UNPACK%d>", D, C::R, JT, C::NR, C::NF, C::NUNP);
+    h->last_variant = name;
+    return DDCB200_OK;
+}
+
 template <int D>
 int launch_w10_j(ddcb200* h, RunParams& p, cudaStream_t st, double step, int jt) {
     switch (jt) {
@@ -586,6 +607,7 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         p.n_tap_blocks = jt;
         p.m_begin = 0;
         // fast-FIR variant where a thread has R = 8 outputs (D = 16); option "variant" 7 forces it, 5 forces the direct form
+        if (D == 16 && jt == 16 && h->force_variant == 10) return launch_w10s<16, 16>(h, p, st, step);   // warp-specialised
         if ((D == 16 && h->force_variant != 5) || h->force_variant == 7) {
             switch (D) {
                 case 16: return launch_w10_j<16>(h, p, st, step, jt);
