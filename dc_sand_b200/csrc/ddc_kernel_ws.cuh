@@ -1,0 +1,257 @@
+// Fast-FIR fused DDC for LARGE decimations (D = 32, 64) -- "kernel WS" (sliced).
+//
+// The fast-FIR kernel (ddc_kernel_w.cuh) needs R = 8 outputs per thread so that one tap fetch feeds four FFMA2; with
+// thread-rows of 128 samples that only holds at D = 16 (at D = 32 / 64 the phase-major kernels have R = 4 / 2 and run at
+// 75 % / 43 % of the FP32 peak when the filter is long).  Making the thread-row 8 D samples long would make a chunk
+// 32 / 64 KB, which no 8-warp ring of shared memory holds.  Instead the chunk is staged in SLICES: slice q holds, for
+// every D-sample block, only the 16 samples [16 q, 16 q + 16) -- exactly the samples that phase groups 4q .. 4q+3 need.
+// A slice of a chunk is 32 (+4 halo) rows of 8 blocks x 16 floats: the SAME shared-memory image as a D = 16 chunk, so
+// the D = 16 inner loop runs on it unchanged (taps of phases 16 q ..).  A warp walks the D / 16 slices of its chunk one
+// after the other, accumulating in registers, then stores.  The strided gather (64 contiguous bytes out of every 4 D) is
+// a 5-D TMA tensor copy: dims (16 floats, D/16 slices, 8 blocks, thread-rows, streams), box (16, 1, 1, 36, 1) = 2304 B;
+// out-of-range thread-rows are zero-filled by the TMA unit, which also takes care of stream tails.
+#pragma once
+#include <cuda.h>
+
+#include "ddc_kernel_w.cuh"
+
+namespace ddck {
+
+template <int D, int JT>
+struct WSCfg {
+    static_assert(D == 32 || D == 64, "sliced staging is for D = 32, 64");
+    static_assert(JT % 2 == 0 && JT <= 32, "tap blocks: even, at most 32 (halo of four thread-rows)");
+    static constexpr int LPQ = D / 16;             // slices per chunk
+    static constexpr int DB = 16;                  // floats of one block inside a slice
+    static constexpr int R = 8;                    // outputs (= blocks) per thread-row
+    static constexpr int ROW = R * DB;             // floats of one thread-row inside a slice (128)
+    static constexpr int V = 4;                    // phase groups per slice
+    static constexpr int JP = JT < 16 ? JT : 16;   // tap blocks per pass
+    static constexpr int NJG = JT / JP;            // passes per slice
+    static_assert(JT % JP == 0, "long filters are padded to a multiple of 16 tap blocks");
+    static constexpr int RH = R / 2;
+    static constexpr int NWP = R + JP - 1;         // register window of one pass (blocks)
+    static constexpr int WROWS = (NWP - 1) / R + 1;
+    // Tensor-mode TMA needs 128-byte aligned shared-memory destinations, so the 16-byte pad that rotates banks in the 1-D
+    // kernels is not available.  Instead one TMA box is the slice of ONE block index for all 36 thread-rows of a slot:
+    // 36 lines of 64 bytes (the inner box dimension), written with the 64-byte swizzle -- the 16-byte unit index
+    // (address bits 4-5) is XORed with address bits 7-8, i.e. with (row / 2) % 4, and bit 6 is row % 2.  Lane L owns
+    // thread-row L, so the eight lanes of a quarter warp read eight consecutive lines at the same logical unit and hit
+    // eight distinct bank groups.  Tiles are 512-byte aligned (2304 bytes of data in a 2560-byte pitch).
+    // (The 128-byte swizzle pads every 64-byte box row to a 128-byte line: tools/microbench/tma_swizzle_probe.cu.)
+    static constexpr int SLOT_ROWS = 36;           // 32 + up to 4 halo rows
+    static constexpr int TILE_BYTES = 2560;        // per block index: 36 x 64 B, rounded up to a multiple of 512
+    static constexpr int SLOT_BYTES = R * TILE_BYTES;          // 20 KB
+    static constexpr int TX_BYTES = R * SLOT_ROWS * 64;        // bytes landed per slot: 18 KB
+    static constexpr int HDR_BYTES = 1024;
+    static constexpr int NGROUPS = 8, NWARPS = 8, NPROD = 2;
+    static constexpr int NSLOT = (227 * 1024 - HDR_BYTES - 1024) / SLOT_BYTES;   // 11
+    static_assert(NSLOT >= NGROUPS + 2 && NSLOT <= 16, "ring size");
+    static constexpr int CHUNK_ROWS = 32;
+    static constexpr int CHUNK_OUT = CHUNK_ROWS * R;       // 256 outputs
+    static constexpr int CHUNK_BLOCKS = CHUNK_ROWS * R;    // 256 D-sample blocks
+    static constexpr int NTW = 3 * (JT / 2) * D;           // complex taps (kernel W layout)
+    static constexpr int SMEM = HDR_BYTES + NSLOT * SLOT_BYTES + 1024;   // + slack to align the slots to 1 KB at run time
+    static_assert(SMEM <= 227 * 1024, "shared memory");
+    __host__ __device__ static constexpr int sub_count(int pr) { return pr == 0 ? (NSLOT + 1) / 2 : NSLOT / 2; }
+    __host__ __device__ static constexpr int sub_base(int pr) { return pr == 0 ? 0 : (NSLOT + 1) / 2; }
+};
+
+// 5-D tensor copy global -> shared (SASS: UTMALDG), completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_5d(void* dst_smem, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, int c4,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// Work items of a CTA are POSITIONS: position = (round * LPQ + q) * 8 + w  <->  slice q of the chunk that compute warp w
+// handles in its round-th turn (local chunk index round * 8 + w).  Producer p stages positions = p (mod 2) in order, into
+// its own sub-ring; warp w consumes positions w, w + 8, ...: consumption order matches staging order.
+template <int D, int JT>
+__global__ void __launch_bounds__(WSCfg<D, JT>::NWARPS * 32 + 32 * WSCfg<D, JT>::NPROD, 1)
+ddc_fused_ws_kernel(const __grid_constant__ RunParams p, const __grid_constant__ CUtensorMap tmap,
+                    const __grid_constant__ TapsParam<WSCfg<D, JT>::NTW> taps) {
+    using C = WSCfg<D, JT>;
+    constexpr int R = C::R, NW = C::NWP, NWARPS = C::NWARPS, NG = C::NGROUPS, NSLOT = C::NSLOT, RH = C::RH;
+    constexpr int LPQ = C::LPQ, JP = C::JP, NJG = C::NJG, ROW = C::ROW;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* empty_bar = full_bar + 16;
+    volatile int* slot_seq = reinterpret_cast<volatile int*>(smem_raw + 384);
+    // the swizzle is a function of the shared-window address: align the slots to 1 KB in that address space
+    unsigned char* buf = smem_raw + C::HDR_BYTES + ((1024u - ((smem_u32(smem_raw) + C::HDR_BYTES) & 1023u)) & 1023u);
+
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int lane = tid & 31;
+    if (tid == 0) {
+#pragma unroll 1
+        for (int s = 0; s < NSLOT; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+            slot_seq[s] = -1;
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int cps = (int)p.tiles_per_stream;   // chunks per stream
+    const int n_k = (int)((p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // chunks of this CTA
+    // positions of this CTA: full rounds of 8 chunks, the last round may be partial (position exists iff its chunk does)
+    const int n_rounds = (n_k + NG - 1) / NG;
+    const int n_pos = n_rounds * LPQ * NG;
+    const unsigned long long chunk_dph = (unsigned long long)((long long)C::CHUNK_OUT * D) * p.step_fx;
+
+    if (warp >= NWARPS) {
+        // ------------------------------------------------------------------ producer warps
+        const int pid = warp - NWARPS;
+        const int sbase = C::sub_base(pid), scnt = C::sub_count(pid);
+        int sidx = 0;
+        uint32_t par = 1;
+        for (int pos = pid; pos < n_pos; pos += C::NPROD) {
+            const int w = pos % NG, q = (pos / NG) % LPQ, round = pos / (NG * LPQ);
+            const int k = round * NG + w;               // local chunk index
+            if (k >= n_k) continue;                     // partial last round: this warp has no chunk (consumers skip it too)
+            const long long gk = blockIdx.x + (long long)k * gridDim.x;   // global chunk
+            const int cs = (int)(gk / cps), cc = (int)(gk % cps);
+            const int slot = sbase + sidx;
+            if (elect_one()) {
+                mbar_wait(&empty_bar[slot], par);
+                slot_seq[slot] = pos;
+                unsigned char* dst = buf + (size_t)slot * C::SLOT_BYTES;
+                mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)C::TX_BYTES);
+                const int row0 = cc * C::CHUNK_ROWS;   // first thread-row (8 blocks) of the chunk inside its stream
+                // NOT fully unrolled: eight UTMALDG in a row need so many uniform registers that ptxas stops using the uniform
+                // datapath for the whole kernel -- the consumers' tap fetches turn from LDCU into per-thread LDC (2.2x slower)
+#pragma unroll 4
+                for (int b = 0; b < R; ++b) tma_load_5d(dst + b * C::TILE_BYTES, &tmap, 0, q, b, row0, cs, &full_bar[slot]);
+            }
+            __syncwarp();
+            if (++sidx == scnt) { sidx = 0; par ^= 1u; }
+        }
+    } else {
+        // ------------------------------------------------------------------ compute warps
+        const int grp = warp;
+        const int g = lane;   // lane L owns thread-row L of the chunk (see WSCfg)
+        // window of a pass: blocks 0 .. NW-1 of thread-rows grow, grow+1, ...; phase group pgv.  Block blk of row `row` lives in
+        // tile blk at line `row`, logical 16-byte unit pgv, physical unit pgv ^ ((row / 2) % 4).
+        auto load_window = [&](float4(&w)[NW], const unsigned char* sb, int grow, int pgv) {
+            int a[C::WROWS];
+#pragma unroll
+            for (int h = 0; h < C::WROWS; ++h) {
+                const int row = grow + h;
+                a[h] = row * 64 + ((pgv ^ ((row >> 1) & 3)) << 4);
+            }
+#pragma unroll
+            for (int b = 0; b < NW; ++b) w[b] = *reinterpret_cast<const float4*>(sb + a[b / R] + (b % R) * C::TILE_BYTES);
+        };
+        float2 rot_thr[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) rot_thr[r] = nco_rot((unsigned long long)((long long)(g * R + r) * D) * p.step_fx);
+
+        // my positions are the (grp / 2)-th, (grp / 2 + 4)-th, ... of producer grp % 2, but only positions whose chunk exists
+        // are staged, so the slot cursor advances per staged position
+        const int sbase = C::sub_base(grp % C::NPROD), scnt = C::sub_count(grp % C::NPROD);
+
+        float2 yprev[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) yprev[r] = make_float2(0.f, 0.f);
+        long long prev_m0 = 0;
+        float2* prev_o = p.out;
+        int prev_cc = 0;
+        long long prev_nout = 0;   // 0 disables the stores
+        float2 m0a[RH], m1a[RH], m2a[RH];
+
+        // The slice loop is a plain counted loop INSIDE the chunk loop so that q (and the tap pointer derived from it) is
+        // warp-uniform for the compiler; derived from a position index that involves the warp number it becomes a per-thread
+        // value and the taps are fetched with per-thread LDC instead of LDCU -> uniform registers (measured: 2.2x slower).
+        for (int round = 0; round < n_rounds; ++round) {
+            const int k = round * NG + grp;
+            if (k >= n_k) break;   // no chunk for this warp in the (partial) last round
+#pragma unroll 1
+          for (int q = 0; q < LPQ; ++q) {
+            const int pos = (round * LPQ + q) * NG + grp;
+            // slot of this position: index among the positions staged by my producer.  In a full round every position is staged;
+            // in the partial last round only those of warps < n_k % 8.  Staged positions before `pos` on my producer:
+            int staged;
+            {
+                const int per_slice_full = NG / C::NPROD;                                  // staged per (round, slice) and producer, full rounds
+                const int last_cnt = n_k - (n_rounds - 1) * NG;                            // chunks in the last round (1 .. 8)
+                const int par2 = grp % C::NPROD;
+                const int per_slice_last = (last_cnt - par2 + C::NPROD - 1) / C::NPROD;    // warps w < last_cnt with w % 2 == par2
+                if (round < n_rounds - 1) staged = (round * LPQ + q) * per_slice_full + grp / C::NPROD;
+                else staged = (n_rounds - 1) * LPQ * per_slice_full + q * per_slice_last + grp / C::NPROD;
+            }
+            const int slot = sbase + staged % scnt;
+            const uint32_t par = (uint32_t)(staged / scnt) & 1u;
+            spin_until_eq_uni(&slot_seq[slot], pos);
+            mbar_wait_uni(&full_bar[slot], par);
+            const unsigned char* sbuf = buf + (size_t)slot * C::SLOT_BYTES;
+            if (q == 0) {
+#pragma unroll
+                for (int r = 0; r < RH; ++r) m0a[r] = m1a[r] = m2a[r] = make_float2(0.f, 0.f);
+            }
+            // taps of slice q: phases 16 q .. 16 q + 15 -> float4 offset 8 q in every (i, seq) set
+            // taps of slice q: phases 16 q .. 16 q + 15 -> float4 offset 8 q in every (i, seq) set (q must stay warp-uniform:
+            // hence the .uni waits above)
+            const float4* tp = &taps.c2[8 * q];
+            int pgv = 0;
+            {   // first pass of the slice; it carries the previous chunk's epilogue (stores enabled only once per chunk)
+                float4 w[NW];
+                load_window(w, sbuf, g, 0);
+                w_epilogue<R>(yprev, rot_thr, p.phase0_fx + (unsigned long long)prev_cc * chunk_dph, prev_m0, prev_o,
+                              q == 0 ? prev_nout : 0);
+                w_fir_pg<D, JP, R>(w, tp, m0a, m1a, m2a);
+                pgv = 1;
+                tp += 2;
+            }
+            {
+                int grow = g;
+                int pgi = 1;
+#pragma unroll 1
+                for (int pass = 1; pass < NJG * C::V; ++pass) {
+                    asm volatile("" : "+r"(pgv), "+r"(grow));   // per-thread copies, hidden from the uniform induction variables
+                    float4 w[NW];
+                    load_window(w, sbuf, grow, pgv);
+                    w_fir_pg<D, JP, R>(w, tp, m0a, m1a, m2a);
+                    ++pgi;
+                    ++pgv;
+                    tp += 2;
+                    if (pgi == C::V) {
+                        pgi = 0;
+                        pgv = 0;
+                        grow += JP / R;
+                        tp += 3 * (JP / 2) * (D / 2) - 2 * C::V;   // first tap set of the next group of 16 tap blocks, phase group 0
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[slot]);
+
+            if (q == LPQ - 1) {
+                // chunk complete: combine the three half-rate sums and hand them to the deferred epilogue
+                const long long gk = blockIdx.x + (long long)k * gridDim.x;
+                const int cs = (int)(gk / cps), cc = (int)(gk % cps);
+#pragma unroll
+                for (int r = 0; r < RH; ++r) {
+                    yprev[2 * r] = make_float2(m0a[r].x + m1a[r].x, m0a[r].y + m1a[r].y);
+                    yprev[2 * r + 1] = make_float2(m1a[r].x - m2a[r].x, m1a[r].y - m2a[r].y);
+                }
+                prev_cc = cc;
+                prev_m0 = (long long)cc * C::CHUNK_OUT + g * R;
+                prev_o = p.out + (long long)cs * p.out_stride + prev_m0;
+                prev_nout = p.n_out;
+            } else if (q == 0) {
+                prev_nout = 0;   // the pending epilogue has been issued with this slice's first pass
+            }
+          }
+        }
+        w_epilogue<R>(yprev, rot_thr, p.phase0_fx + (unsigned long long)prev_cc * chunk_dph, prev_m0, prev_o, prev_nout);
+    }
+}
+
+}  // namespace ddck

@@ -17,6 +17,7 @@
 #include "ddc_kernels.cuh"
 #include "ddc_kernel_p.cuh"
 #include "ddc_kernel_w.cuh"
+#include "ddc_kernel_ws.cuh"
 
 using namespace ddck;
 
@@ -521,6 +522,76 @@ int launch_wq_j(ddcb200* h, RunParams& p, cudaStream_t st, double step, int jt) 
     return fail(DDCB200_EINVAL, "small-decimation kernel: unsupported tap-block count %d", jt);
 }
 
+// ---- kernel WS (sliced staging, D = 32 / 64): tensor map over the input + launch -------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(sym);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// dims (fastest first): 16 floats of a slice, D/16 slices, 8 blocks of a thread-row, thread-rows, streams;
+// box = (16, 1, 1, 36, 1): the slice of one block index for the 36 thread-rows of a slot, 64-byte lines, 64-byte swizzle
+int make_slice_tmap(const float* d_in, int D, long long n_rows, long long n_streams, long long in_stride, CUtensorMap* out) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return fail(DDCB200_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t gdim[5] = {16, (cuuint64_t)(D / 16), 8, (cuuint64_t)n_rows, (cuuint64_t)n_streams};
+    const cuuint64_t gstr[4] = {64, (cuuint64_t)D * 4, (cuuint64_t)D * 32, (cuuint64_t)in_stride * 4};
+    const cuuint32_t box[5] = {16, 1, 1, 36, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(d_in), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DDCB200_ECUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+    return DDCB200_OK;
+}
+
+template <int D, int JT>
+int launch_ws(ddcb200* h, RunParams& p, const float* d_in, long long n_rows, cudaStream_t st, double step) {
+    using C = WSCfg<D, JT>;
+    auto kern = ddc_fused_ws_kernel<D, JT>;
+    static bool attr_set[64] = {};
+    if (h->device < 64 && !attr_set[h->device]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        attr_set[h->device] = true;
+    }
+    CUtensorMap tmap;
+    int rc = make_slice_tmap(d_in, D, n_rows, p.n_streams, p.in_stride, &tmap);
+    if (rc) return rc;
+    TapsParam<C::NTW> tp;
+    std::memcpy(tp.c2, cached_wtaps(h, step, JT, D), sizeof(float2) * (size_t)C::NTW);
+    const long long grid = std::min<long long>(p.total_tiles, h->sm_count);
+    kern<<<(unsigned)grid, C::NWARPS * 32 + 32 * C::NPROD, C::SMEM, st>>>(p, tmap, tp);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    char name[96];
+    snprintf(name, sizeof(name), "fused_fast_fir_sliced<D%d,R%d,J%d,SLICES%d,SLOTS%d>", D, C::R, JT, C::LPQ, C::NSLOT);
+    h->last_variant = name;
+    return DDCB200_OK;
+}
+
+template <int D>
+int launch_ws_j(ddcb200* h, RunParams& p, const float* d_in, long long n_rows, cudaStream_t st, double step, int jt) {
+    switch (jt) {
+        case 8: return launch_ws<D, 8>(h, p, d_in, n_rows, st, step);
+        case 16: return launch_ws<D, 16>(h, p, d_in, n_rows, st, step);
+        case 32: return launch_ws<D, 32>(h, p, d_in, n_rows, st, step);
+        default: return fail(DDCB200_EINVAL, "sliced kernel: unsupported tap-block count %d", jt);
+    }
+}
+
 template <int D>
 int launch_p_j(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, int jt, int ks) {
     if (ks == 2) {
@@ -624,8 +695,40 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         }
     }
 
+    // ---- large decimations (D = 32, 64): sliced staging (ddc_kernel_ws.cuh), fast FIR with R = 8 outputs per thread ----------
+    // Auto: where the direct form is FP32-bound (4 T / D flop per sample against 4 + 8 / D bytes at the measured ridge of
+    // 11.4 flop/B); HBM-bound cells stay on the phase-major kernel, which over-fetches nothing.  Option "variant" 11 forces it.
+    long long m_done = 0;
+    bool sliced_done = false;
+    {
+        const int Jp = (T + D - 1) / D;
+        const bool fp32_bound = 4.0 * T / D > 11.4 * (4.0 + 8.0 / D);
+        if (aligned_f32(d_in, in_stride, packed) && (D == 32 || D == 64) && Jp <= 32 && T >= D &&
+            (h->force_variant == 11 || (h->force_variant == 0 && fp32_bound))) {
+            const int jt = Jp <= 8 ? 8 : (Jp <= 16 ? 16 : 32);
+            const long long n_blocks = (n_samples / (8LL * D)) * 8;         // whole thread-rows of 8 blocks: the tensor map covers exactly these
+            long long m_f = n_blocks * D >= T ? (n_blocks * D - T) / D + 1 : 0;   // outputs whose window lies inside them
+            if (m_f > M) m_f = M;
+            if (m_f > 0) {
+                const long long m_all = p.n_out;
+                p.n_out = m_f;
+                p.tiles_per_stream = (m_f + 255) / 256;
+                p.total_tiles = p.tiles_per_stream * n_streams;
+                p.n_taps = jt * D;
+                p.n_tap_blocks = jt;
+                p.m_begin = 0;
+                int rc2 = D == 32 ? launch_ws_j<32>(h, p, reinterpret_cast<const float*>(d_in), n_blocks / 8, st, step, jt)
+                                  : launch_ws_j<64>(h, p, reinterpret_cast<const float*>(d_in), n_blocks / 8, st, step, jt);
+                if (rc2) return rc2;
+                p.n_out = m_all;
+                m_done = m_f;
+                sliced_done = true;
+            }
+        }
+    }
+
     // ---- small decimations (D = 4, 8): NQ = 16 / D interleaved decimate-by-16 fast FIRs with shifted tap sets --------------
-    if (aligned_f32(d_in, in_stride, packed) && (D == 4 || D == 8) && (h->force_variant == 0 || h->force_variant == 7)) {
+    if (!sliced_done && aligned_f32(d_in, in_stride, packed) && (D == 4 || D == 8) && (h->force_variant == 0 || h->force_variant == 7)) {
         const int nq = 16 / D;
         const int Tq = T + D * (nq - 1);
         const int jneed = (Tq + 15) / 16;
@@ -644,7 +747,7 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
     // ---- kernel P (phase-major, R = 128/D outputs per thread): short polyphase branches, J = ceil(T/D) <= 16 ------
     const bool long_w = D == 16 && (T + D - 1) / D > 16 && (T + D - 1) / D <= 64 &&
                         (h->force_variant == 0 || h->force_variant == 7 || h->force_variant == 9);
-    if (aligned_f32(d_in, in_stride, packed) && (D == 16 || D == 32 || D == 64) && ((T + D - 1) / D <= 16 || long_w) &&
+    if (!sliced_done && aligned_f32(d_in, in_stride, packed) && (D == 16 || D == 32 || D == 64) && ((T + D - 1) / D <= 16 || long_w) &&
         (h->force_variant == 0 || (h->force_variant >= 5 && h->force_variant <= 9))) {
         const int ksp = (h->force_variant == 6) ? 2 : 1;   // option "variant": 5 (= auto) one warp per chunk, 6 = two (slower)
         const int Jp = (T + D - 1) / D;
@@ -686,8 +789,7 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
     make_ctaps(h, step, (int)ct.size(), ct.data());
 
     int rc = DDCB200_OK;
-    long long m_done = 0;
-    if (tiles > 0) {
+    if (tiles > 0 && !sliced_done) {
         p.tiles_per_stream = tiles;
         p.total_tiles = tiles * n_streams;
         p.n_taps = n_taps_pad;
@@ -725,7 +827,7 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(h->ring_ev[slot], st));
         h->launches++;
-        if (tiles == 0) h->last_variant = packed ? "generic<packed10>" : "generic<f32>";
+        if (tiles == 0 && !sliced_done) h->last_variant = packed ? "generic<packed10>" : "generic<f32>";
     }
     return DDCB200_OK;
 }

@@ -327,3 +327,23 @@ def test_runtime_tap_reload_and_narrowband_mode(taps_dir):
         tp = genfromtxt(os.path.join(taps_dir, csv), delimiter=",")
         emax, el2 = rel_err(y, orc.ddc_reference(x, fc, tp, d, FS))
         assert emax <= TOL_MAX and el2 <= TOL_L2, (d, emax, el2)
+
+
+@pytest.mark.parametrize("d,t,streams", [(32, 512, 3), (32, 1024, 1), (64, 1024, 2), (64, 300, 1)])
+def test_sliced_staging_kernel_large_decimations(d, t, streams, tmp_path):
+    """D = 32 / 64 through the sliced-staging fast-FIR kernel (strided 5-D TMA gather, 64-byte swizzle): several streams,
+    a length that is not a multiple of the 8 D-sample thread-row (tail outputs come from the generic kernel), and the
+    kernel forced on an HBM-bound cell as well."""
+    from scipy import signal
+
+    n = 8 * d * 300 + 5 * d + 8          # rows stay 16-byte aligned (n % 4 == 0) but are not whole thread-rows
+    tp = signal.firwin(t, 0.8 / d)
+    ddc = DigitalDownConverter(d, FS, _custom_taps(tmp_path, tp))
+    ddc.set_option("variant", 11)
+    xs = np.stack([synth.digitiser_stream(n, 500 + d + s) for s in range(streams)]).astype(np.float32)
+    y = ddc.run_tensor(torch.from_numpy(xs).cuda(), 100e6).cpu().numpy()
+    assert "sliced" in ddc.last_variant, ddc.last_variant
+    ref = np.stack([orc.ddc_reference(r, 100e6, tp, d, FS) for r in xs])
+    emax, el2 = rel_err(y, ref)
+    k = 4 if t > 256 else 1
+    assert y.shape == ref.shape and emax <= k * TOL_MAX and el2 <= k * TOL_L2, (emax, el2)
