@@ -142,12 +142,32 @@ def _cpu_call(args):
     return time.perf_counter() - t0, len(y)
 
 
+def _cpu_fir_only(n):
+    """Time of the FIR + decimation stages alone (ddc.py:98,119) on an already mixed complex64 array, one thread."""
+    from scipy import signal
+
+    from dc_sand_b200 import synth, taps
+    from oracle import ddc_oracle as orc
+
+    x = synth.digitiser_stream(n, 7).astype(np.float32)
+    tp = taps.coefficients("ddc_coeff_107MHz.csv")
+    mix = x * orc.nco(n, FC, FS)
+    best = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter()
+        y = (signal.convolve(mix, tp, mode="valid") / sum(tp))[0::D]
+        best = min(best, time.perf_counter() - t0)
+    return best, len(y)
+
+
 def cpu_baseline_single_core(n_calls=6, n=1 << 20):
     """The faithful restatement of the reference's run() (incl. its zero-scaled noise draw), one thread."""
     _cpu_call((1, n))  # warm-up
     t = [_cpu_call((2 + i, n))[0] for i in range(n_calls)]
     best = min(t)
+    fir_s, _ = _cpu_fir_only(n)
     return {
+        "fir_only_value": n / fir_s / 1e9,   # SURVEY 8d: the FIR + decimate stages without NCO / noise generation
         "value": n / best / 1e9,
         "unit": "Gsamples/s",
         "cores": 1,

@@ -32,6 +32,11 @@ SIGNATURES = {
     "ddcb200_cwg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_double,
                               C.c_int64, C.c_int, C.c_double, C.c_uint64, C.c_void_p]),
     "ddcb200_session_open": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.POINTER(C.c_void_p)]),
+    "ddcb200_session_open_packed10": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.POINTER(C.c_void_p)]),
+    "ddcb200_session_push_packed10": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                                C.POINTER(C.c_int64), C.c_void_p]),
+    "ddcb200_session_push_host_packed10": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                                     C.POINTER(C.c_int64)]),
     "ddcb200_session_close": (None, [C.c_void_p]),
     "ddcb200_session_reset": (C.c_int, [C.c_void_p, C.c_int64]),
     "ddcb200_session_pending": (C.c_int64, [C.c_void_p]),

@@ -1237,16 +1237,18 @@ struct ddcb200_session {
     ddcb200* h = nullptr;
     int64_t n_streams = 0, max_chunk = 0;
     double step = 0.0;
-    int64_t carry = 0;     // samples of every stream waiting at the head of work[cur]
+    bool packed = false;   // work buffers hold packed 10-bit bytes (5 per 4 samples) instead of float32
+    int64_t carry = 0;     // samples of every stream waiting at the head of work[cur] (a multiple of 4 when packed)
     int64_t abs0 = 0;      // absolute index of the first carried sample (always a multiple of D)
-    int64_t pitch = 0;     // floats per stream row of a work buffer (multiple of 4: rows stay 16-byte aligned)
+    int64_t pitch = 0;     // BYTES per stream row of a work buffer (multiple of 16: rows stay 16-byte aligned)
     int64_t out_cap = 0;   // outputs per stream a push of max_chunk samples can produce
-    float* work[2] = {};
+    unsigned char* work[2] = {};
     ddcb200_c64* dout[2] = {};
     cudaEvent_t ev_in[2] = {}, ev_k[2] = {}, ev_out[2] = {};
     cudaEvent_t ev_user = nullptr;   // end of the last asynchronous device push (on the caller's stream)
     bool user_pending = false;
     int cur = 0;
+    size_t bytes(int64_t samples) const { return packed ? (size_t)(samples / 4 * 5) : (size_t)samples * 4; }
 };
 
 namespace {
@@ -1259,46 +1261,50 @@ int stream_step(ddcb200_session* s, int64_t n, ddcb200_c64* d_out, int64_t out_s
     int64_t m = 0;
     if (have >= T) {
         m = (have - T) / D + 1;
-        int rc = run_device(h, s->work[s->cur], false, have, s->n_streams, s->pitch, s->step, s->abs0, d_out, out_stride, st);
+        int rc = run_device(h, s->work[s->cur], s->packed, have, s->n_streams, s->packed ? s->pitch : s->pitch / 4, s->step, s->abs0,
+                            d_out, out_stride, st);
         if (rc) return rc;
     }
     const int64_t used = m * D, rest = have - used;
     if (rest > 0 && used > 0)
-        CUDA_TRY(cudaMemcpy2DAsync(s->work[s->cur ^ 1], (size_t)s->pitch * 4, s->work[s->cur] + used, (size_t)s->pitch * 4,
-                                   (size_t)rest * 4, (size_t)s->n_streams, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpy2DAsync(s->work[s->cur ^ 1], (size_t)s->pitch, s->work[s->cur] + s->bytes(used), (size_t)s->pitch,
+                                   s->bytes(rest), (size_t)s->n_streams, cudaMemcpyDeviceToDevice, st));
     if (used > 0) s->cur ^= 1;
     s->carry = rest;
     s->abs0 += used;
     *n_out = m;
     return DDCB200_OK;
 }
-}  // namespace
 
-int ddcb200_session_open(ddcb200_t* h, int64_t n_streams, int64_t max_chunk_samples, double phase_step_cycles,
-                        ddcb200_session_t** out) {
+int session_open(ddcb200_t* h, int64_t n_streams, int64_t max_chunk_samples, double phase_step_cycles, bool packed,
+                 ddcb200_session_t** out) {
     if (!h || !out || n_streams <= 0 || n_streams > 65535 || max_chunk_samples <= 0)
         return fail(DDCB200_EINVAL, "session_open: bad arguments");
     *out = nullptr;
     DeviceGuard g(h->device);
     const int T = (int)h->taps.size(), D = h->decim;
     if (T < D) return fail(DDCB200_EINVAL, "session_open: streaming needs n_taps (%d) >= decimation (%d)", T, D);
+    if (packed && (D % 4)) return fail(DDCB200_EINVAL, "session_open: packed streaming needs a decimation that is a multiple of 4");
     auto* s = new (std::nothrow) ddcb200_session();
     if (!s) return fail(DDCB200_ENOMEM, "session_open: out of host memory");
     s->h = h;
     s->n_streams = n_streams;
+    s->packed = packed;
     s->max_chunk = std::max<int64_t>(max_chunk_samples, (int64_t)T);
+    if (packed) s->max_chunk = (s->max_chunk + 3) / 4 * 4;
     s->step = phase_step_cycles;
-    s->pitch = ((int64_t)(T + D) + s->max_chunk + 3) / 4 * 4;
+    const int64_t row_samples = ((int64_t)(T + D) + s->max_chunk + 63) / 64 * 64;   // 64 samples = 256 B float32 = 80 B packed
+    s->pitch = (int64_t)s->bytes(row_samples);
     s->out_cap = (s->max_chunk + T + D) / D + 1;
     for (int i = 0; i < 2; ++i) {
-        if (cudaMalloc(&s->work[i], (size_t)s->pitch * 4 * (size_t)n_streams) != cudaSuccess ||
+        if (cudaMalloc(&s->work[i], (size_t)s->pitch * (size_t)n_streams) != cudaSuccess ||
             cudaMalloc(&s->dout[i], (size_t)s->out_cap * sizeof(ddcb200_c64) * (size_t)n_streams) != cudaSuccess ||
             cudaEventCreateWithFlags(&s->ev_in[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&s->ev_k[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&s->ev_out[i], cudaEventDisableTiming) != cudaSuccess) {
             cudaGetLastError();
             ddcb200_session_close(s);
-            return fail(DDCB200_ENOMEM, "session_open: device allocation failed (%lld streams x %lld samples)",
+            return fail(DDCB200_ENOMEM, "session_open: device allocation failed (%lld streams x %lld bytes)",
                         (long long)n_streams, (long long)s->pitch);
         }
     }
@@ -1309,6 +1315,89 @@ int ddcb200_session_open(ddcb200_t* h, int64_t n_streams, int64_t max_chunk_samp
     }
     *out = s;
     return DDCB200_OK;
+}
+
+// device-pointer push; in_stride in elements of the input type (floats, or bytes when packed)
+int session_push_dev(ddcb200_session_t* s, const void* d_in, bool packed, int64_t n_samples, int64_t in_stride, ddcb200_c64* d_out,
+                     int64_t out_stride, int64_t* n_out, void* cuda_stream) {
+    if (!s || !d_in || !n_out || n_samples <= 0) return fail(DDCB200_EINVAL, "session_push: bad arguments");
+    if (packed != s->packed) return fail(DDCB200_EINVAL, "session_push: this session was opened for %s input", s->packed ? "packed" : "float32");
+    if (packed && (n_samples % 4)) return fail(DDCB200_EINVAL, "session_push: packed pushes need n_samples %% 4 == 0");
+    if (n_samples > s->max_chunk) return fail(DDCB200_EINVAL, "session_push: %lld samples > max_chunk_samples %lld",
+                                              (long long)n_samples, (long long)s->max_chunk);
+    const int64_t m = ddcb200_session_out_len(s, n_samples);
+    if (m > 0 && (!d_out || out_stride < m)) return fail(DDCB200_EINVAL, "session_push: output too small for %lld outputs", (long long)m);
+    DeviceGuard g(s->h->device);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : s->h->stream;
+    CUDA_TRY(cudaMemcpy2DAsync(s->work[s->cur] + s->bytes(s->carry), (size_t)s->pitch, d_in, (size_t)in_stride * (packed ? 1 : 4),
+                               s->bytes(n_samples), (size_t)s->n_streams, cudaMemcpyDeviceToDevice, st));
+    int rc = stream_step(s, n_samples, d_out, out_stride, n_out, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(s->ev_user, st));
+    s->user_pending = true;
+    return DDCB200_OK;
+}
+
+int session_push_host(ddcb200_session_t* s, const void* h_in, bool packed, int64_t n_samples, int64_t in_stride, ddcb200_c64* h_out,
+                      int64_t out_stride, int64_t* n_out) {
+    if (!s || !h_in || !n_out || n_samples <= 0) return fail(DDCB200_EINVAL, "session_push_host: bad arguments");
+    if (packed != s->packed) return fail(DDCB200_EINVAL, "session_push_host: this session was opened for %s input", s->packed ? "packed" : "float32");
+    if (packed && (n_samples % 4)) return fail(DDCB200_EINVAL, "session_push_host: packed pushes need n_samples %% 4 == 0");
+    const int64_t m_total = ddcb200_session_out_len(s, n_samples);
+    if (m_total > 0 && (!h_out || out_stride < m_total)) return fail(DDCB200_EINVAL, "session_push_host: output too small");
+    ddcb200* h = s->h;
+    DeviceGuard g(h->device);
+    // Pieces of max_chunk samples, two work buffers deep: the H2D copy of piece i + 1 (copy_in stream) runs under the
+    // kernel of piece i (compute stream), the D2H copy of its outputs on copy_out.
+    if (s->user_pending) {   // an asynchronous device push may still be using the work buffers on the caller's stream
+        CUDA_TRY(cudaStreamWaitEvent(h->copy_in, s->ev_user, 0));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, s->ev_user, 0));
+        s->user_pending = false;
+    }
+    const size_t src_pitch = (size_t)in_stride * (packed ? 1 : 4);
+    int64_t done = 0, m_done = 0;
+    bool rec_k[2] = {false, false}, rec_out[2] = {false, false};
+    while (done < n_samples) {
+        const int64_t n = std::min<int64_t>(s->max_chunk, n_samples - done);
+        const int b = s->cur;
+        if (rec_k[b]) CUDA_TRY(cudaStreamWaitEvent(h->copy_in, s->ev_k[b], 0));     // last kernel / tail copy reading work[b]
+        CUDA_TRY(cudaMemcpy2DAsync(s->work[b] + s->bytes(s->carry), (size_t)s->pitch,
+                                   reinterpret_cast<const unsigned char*>(h_in) + s->bytes(done), src_pitch, s->bytes(n),
+                                   (size_t)s->n_streams, cudaMemcpyHostToDevice, h->copy_in));
+        CUDA_TRY(cudaEventRecord(s->ev_in[b], h->copy_in));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, s->ev_in[b], 0));
+        if (rec_out[b]) CUDA_TRY(cudaStreamWaitEvent(h->stream, s->ev_out[b], 0));  // dout[b] has been copied out
+        int64_t m = 0;
+        int rc = stream_step(s, n, s->dout[b], s->out_cap, &m, h->stream);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(s->ev_k[b], h->stream));
+        rec_k[b] = true;
+        if (m > 0) {
+            CUDA_TRY(cudaStreamWaitEvent(h->copy_out, s->ev_k[b], 0));
+            CUDA_TRY(cudaMemcpy2DAsync(h_out + m_done, (size_t)out_stride * sizeof(ddcb200_c64), s->dout[b],
+                                       (size_t)s->out_cap * sizeof(ddcb200_c64), (size_t)m * sizeof(ddcb200_c64),
+                                       (size_t)s->n_streams, cudaMemcpyDeviceToHost, h->copy_out));
+            CUDA_TRY(cudaEventRecord(s->ev_out[b], h->copy_out));
+            rec_out[b] = true;
+        }
+        done += n;
+        m_done += m;
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->copy_out));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->copy_in));
+    *n_out = m_done;
+    return DDCB200_OK;
+}
+}  // namespace
+
+int ddcb200_session_open(ddcb200_t* h, int64_t n_streams, int64_t max_chunk_samples, double phase_step_cycles,
+                         ddcb200_session_t** out) {
+    return session_open(h, n_streams, max_chunk_samples, phase_step_cycles, false, out);
+}
+int ddcb200_session_open_packed10(ddcb200_t* h, int64_t n_streams, int64_t max_chunk_samples, double phase_step_cycles,
+                                  ddcb200_session_t** out) {
+    return session_open(h, n_streams, max_chunk_samples, phase_step_cycles, true, out);
 }
 
 void ddcb200_session_close(ddcb200_session_t* s) {
@@ -1344,69 +1433,20 @@ int64_t ddcb200_session_out_len(ddcb200_session_t* s, int64_t n_samples) {
 }
 
 int ddcb200_session_push_f32(ddcb200_session_t* s, const float* d_in, int64_t n_samples, int64_t in_stride, ddcb200_c64* d_out,
-                            int64_t out_stride, int64_t* n_out, void* cuda_stream) {
-    if (!s || !d_in || !n_out || n_samples <= 0) return fail(DDCB200_EINVAL, "session_push: bad arguments");
-    if (n_samples > s->max_chunk) return fail(DDCB200_EINVAL, "session_push: %lld samples > max_chunk_samples %lld",
-                                              (long long)n_samples, (long long)s->max_chunk);
-    const int64_t m = ddcb200_session_out_len(s, n_samples);
-    if (m > 0 && (!d_out || out_stride < m)) return fail(DDCB200_EINVAL, "session_push: output too small for %lld outputs", (long long)m);
-    DeviceGuard g(s->h->device);
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : s->h->stream;
-    CUDA_TRY(cudaMemcpy2DAsync(s->work[s->cur] + s->carry, (size_t)s->pitch * 4, d_in, (size_t)in_stride * 4, (size_t)n_samples * 4,
-                               (size_t)s->n_streams, cudaMemcpyDeviceToDevice, st));
-    int rc = stream_step(s, n_samples, d_out, out_stride, n_out, st);
-    if (rc) return rc;
-    CUDA_TRY(cudaEventRecord(s->ev_user, st));
-    s->user_pending = true;
-    return DDCB200_OK;
+                             int64_t out_stride, int64_t* n_out, void* cuda_stream) {
+    return session_push_dev(s, d_in, false, n_samples, in_stride, d_out, out_stride, n_out, cuda_stream);
 }
-
+int ddcb200_session_push_packed10(ddcb200_session_t* s, const uint8_t* d_in, int64_t n_samples, int64_t in_stride_bytes,
+                                  ddcb200_c64* d_out, int64_t out_stride, int64_t* n_out, void* cuda_stream) {
+    return session_push_dev(s, d_in, true, n_samples, in_stride_bytes, d_out, out_stride, n_out, cuda_stream);
+}
 int ddcb200_session_push_host_f32(ddcb200_session_t* s, const float* h_in, int64_t n_samples, int64_t in_stride, ddcb200_c64* h_out,
-                                 int64_t out_stride, int64_t* n_out) {
-    if (!s || !h_in || !n_out || n_samples <= 0) return fail(DDCB200_EINVAL, "session_push_host: bad arguments");
-    const int64_t m_total = ddcb200_session_out_len(s, n_samples);
-    if (m_total > 0 && (!h_out || out_stride < m_total)) return fail(DDCB200_EINVAL, "session_push_host: output too small");
-    ddcb200* h = s->h;
-    DeviceGuard g(h->device);
-    // Pieces of max_chunk samples, two work buffers deep: the H2D copy of piece i + 1 (copy_in stream) runs under the
-    // kernel of piece i (compute stream), the D2H copy of its outputs on copy_out.
-    if (s->user_pending) {   // an asynchronous device push may still be using the work buffers on the caller's stream
-        CUDA_TRY(cudaStreamWaitEvent(h->copy_in, s->ev_user, 0));
-        CUDA_TRY(cudaStreamWaitEvent(h->stream, s->ev_user, 0));
-        s->user_pending = false;
-    }
-    int64_t done = 0, m_done = 0;
-    bool rec_k[2] = {false, false}, rec_out[2] = {false, false};
-    while (done < n_samples) {
-        const int64_t n = std::min<int64_t>(s->max_chunk, n_samples - done);
-        const int b = s->cur;
-        if (rec_k[b]) CUDA_TRY(cudaStreamWaitEvent(h->copy_in, s->ev_k[b], 0));     // last kernel / tail copy reading work[b]
-        CUDA_TRY(cudaMemcpy2DAsync(s->work[b] + s->carry, (size_t)s->pitch * 4, h_in + done, (size_t)in_stride * 4, (size_t)n * 4,
-                                   (size_t)s->n_streams, cudaMemcpyHostToDevice, h->copy_in));
-        CUDA_TRY(cudaEventRecord(s->ev_in[b], h->copy_in));
-        CUDA_TRY(cudaStreamWaitEvent(h->stream, s->ev_in[b], 0));
-        if (rec_out[b]) CUDA_TRY(cudaStreamWaitEvent(h->stream, s->ev_out[b], 0));  // dout[b] has been copied out
-        int64_t m = 0;
-        int rc = stream_step(s, n, s->dout[b], s->out_cap, &m, h->stream);
-        if (rc) return rc;
-        CUDA_TRY(cudaEventRecord(s->ev_k[b], h->stream));
-        rec_k[b] = true;
-        if (m > 0) {
-            CUDA_TRY(cudaStreamWaitEvent(h->copy_out, s->ev_k[b], 0));
-            CUDA_TRY(cudaMemcpy2DAsync(h_out + m_done, (size_t)out_stride * sizeof(ddcb200_c64), s->dout[b],
-                                       (size_t)s->out_cap * sizeof(ddcb200_c64), (size_t)m * sizeof(ddcb200_c64),
-                                       (size_t)s->n_streams, cudaMemcpyDeviceToHost, h->copy_out));
-            CUDA_TRY(cudaEventRecord(s->ev_out[b], h->copy_out));
-            rec_out[b] = true;
-        }
-        done += n;
-        m_done += m;
-    }
-    CUDA_TRY(cudaStreamSynchronize(h->copy_out));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->copy_in));
-    *n_out = m_done;
-    return DDCB200_OK;
+                                  int64_t out_stride, int64_t* n_out) {
+    return session_push_host(s, h_in, false, n_samples, in_stride, h_out, out_stride, n_out);
+}
+int ddcb200_session_push_host_packed10(ddcb200_session_t* s, const uint8_t* h_in, int64_t n_samples, int64_t in_stride_bytes,
+                                       ddcb200_c64* h_out, int64_t out_stride, int64_t* n_out) {
+    return session_push_host(s, h_in, true, n_samples, in_stride_bytes, h_out, out_stride, n_out);
 }
 
 }  // extern "C"

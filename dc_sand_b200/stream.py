@@ -18,17 +18,20 @@ from .ddc import DigitalDownConverter, _torch_stream
 
 class DDCStream:
     def __init__(self, ddc: DigitalDownConverter, center_freq: float, n_streams: int = 1, max_chunk: int = 1 << 22,
-                 total_samples: int | None = None) -> None:
+                 total_samples: int | None = None, packed: bool = False) -> None:
+        """`packed=True`: pushes are packed 10-bit bytes (uint8, 5 bytes per 4 samples; the format of
+        DigitalDownConverter.run_packed), unpacked inside the fused kernel."""
         self.ddc = ddc
         self.n_streams = int(n_streams)
         self.max_chunk = int(max_chunk)
+        self.packed = bool(packed)
         if total_samples is None:
             self.phase_step = float(center_freq) / float(ddc.sampling_frequency)
         else:
             self.phase_step = cwg.phase_step_cycles(int(total_samples), center_freq, ddc.sampling_frequency)
         s = C.c_void_p()
-        _lib.check(_lib.load().ddcb200_session_open(ddc._get_handle(), self.n_streams, self.max_chunk, self.phase_step,
-                                                    C.byref(s)), "ddcb200_session_open")
+        opener = _lib.load().ddcb200_session_open_packed10 if self.packed else _lib.load().ddcb200_session_open
+        _lib.check(opener(ddc._get_handle(), self.n_streams, self.max_chunk, self.phase_step, C.byref(s)), "ddcb200_session_open")
         self._s = s
 
     # ------------------------------------------------------------------------------------------------------------
@@ -67,33 +70,46 @@ class DDCStream:
 
     # ------------------------------------------------------------------------------------------------------------
     def push(self, x: np.ndarray) -> np.ndarray:
-        """Host arrays: [n] (one stream) or [streams, n] real samples -> complex64 [m] or [streams, m]; m may be 0.
-        Pieces longer than `max_chunk` are cut and double-buffered inside the library."""
+        """Host arrays: [n] (one stream) or [streams, n] real samples (or uint8 [.., 5 n / 4] for a packed session)
+        -> complex64 [m] or [streams, m]; m may be 0.  Pieces longer than `max_chunk` are cut and double-buffered inside
+        the library."""
         a = np.asarray(x)
         one_d = a.ndim == 1
         a2 = a[None, :] if one_d else a
         if a2.ndim != 2 or a2.shape[0] != self.n_streams or a2.shape[1] == 0:
             raise ValueError(f"push needs [{self.n_streams}, n > 0] samples, got shape {a.shape}")
-        a2 = np.ascontiguousarray(a2, dtype=np.float32)
-        n = a2.shape[1]
+        if self.packed:
+            a2 = np.ascontiguousarray(a2, dtype=np.uint8)
+            if a2.shape[1] % 5:
+                raise ValueError("packed pushes must be whole groups of 5 bytes (4 samples)")
+            n = a2.shape[1] // 5 * 4
+            fn = _lib.load().ddcb200_session_push_host_packed10
+        else:
+            a2 = np.ascontiguousarray(a2, dtype=np.float32)
+            n = a2.shape[1]
+            fn = _lib.load().ddcb200_session_push_host_f32
         m = self.out_len(n)
         out = np.empty((self.n_streams, max(m, 1)), dtype=np.complex64)
         got = C.c_int64(0)
-        _lib.check(_lib.load().ddcb200_session_push_host_f32(self._s, a2.ctypes.data, n, n, out.ctypes.data, out.shape[1],
-                                                             C.byref(got)), "ddcb200_session_push_host_f32")
+        _lib.check(fn(self._s, a2.ctypes.data, n, a2.shape[1], out.ctypes.data, out.shape[1], C.byref(got)),
+                   "ddcb200_session_push_host")
         assert got.value == m
         out = out[:, :m]
         return out[0] if one_d else out
 
     def push_tensor(self, x, out=None):
-        """torch CUDA tensors, asynchronous on torch's current stream: float32 [n] or [streams, n] (n <= max_chunk)."""
+        """torch CUDA tensors, asynchronous on torch's current stream: float32 [n] or [streams, n] (uint8 [.., 5 n / 4] for a
+        packed session), n <= max_chunk."""
         import torch
 
         one_d = x.dim() == 1
         x2 = x.unsqueeze(0) if one_d else x
-        if x2.dim() != 2 or x2.shape[0] != self.n_streams or x2.dtype != torch.float32 or x2.stride(1) != 1:
-            raise ValueError(f"push_tensor needs float32 [{self.n_streams}, n] with contiguous rows")
-        n = x2.shape[1]
+        want = torch.uint8 if self.packed else torch.float32
+        if x2.dim() != 2 or x2.shape[0] != self.n_streams or x2.dtype != want or x2.stride(1) != 1:
+            raise ValueError(f"push_tensor needs {want} [{self.n_streams}, n] with contiguous rows")
+        if self.packed and x2.shape[1] % 5:
+            raise ValueError("packed pushes must be whole groups of 5 bytes (4 samples)")
+        n = x2.shape[1] // 5 * 4 if self.packed else x2.shape[1]
         m = self.out_len(n)
         if out is None:
             out = torch.empty((self.n_streams, m), dtype=torch.complex64, device=x.device)
@@ -101,8 +117,8 @@ class DDCStream:
         if out2.shape[0] != self.n_streams or out2.shape[1] < m or out2.dtype != torch.complex64 or out2.stride(1) != 1:
             raise ValueError("out must be complex64 [streams, >= m] with contiguous rows")
         got = C.c_int64(0)
-        _lib.check(_lib.load().ddcb200_session_push_f32(self._s, x2.data_ptr(), n, x2.stride(0), out2.data_ptr(),
-                                                        max(out2.stride(0), 1), C.byref(got), _torch_stream(torch, x.device)),
-                   "ddcb200_session_push_f32")
+        fn = _lib.load().ddcb200_session_push_packed10 if self.packed else _lib.load().ddcb200_session_push_f32
+        _lib.check(fn(self._s, x2.data_ptr(), n, x2.stride(0), out2.data_ptr(), max(out2.stride(0), 1), C.byref(got),
+                      _torch_stream(torch, x.device)), "ddcb200_session_push")
         res = out2[:, : got.value]
         return res[0] if one_d else res

@@ -147,6 +147,14 @@ int ddcb200_session_push_f32(ddcb200_session_t* s, const float* d_in, int64_t n_
                             ddcb200_c64* d_out, int64_t out_stride, int64_t* n_out, void* cuda_stream);
 int ddcb200_session_push_host_f32(ddcb200_session_t* s, const float* h_in, int64_t n_samples, int64_t in_stride,
                                  ddcb200_c64* h_out, int64_t out_stride, int64_t* n_out);
+/* The same for packed 10-bit input (the stub ddc.py:68-83 fused in): pushes are whole groups of 4 samples (5 bytes),
+ * strides are in bytes, the decimation must be a multiple of 4. */
+int ddcb200_session_open_packed10(ddcb200_t* handle, int64_t n_streams, int64_t max_chunk_samples,
+                                  double phase_step_cycles, ddcb200_session_t** out);
+int ddcb200_session_push_packed10(ddcb200_session_t* s, const uint8_t* d_in, int64_t n_samples, int64_t in_stride_bytes,
+                                  ddcb200_c64* d_out, int64_t out_stride, int64_t* n_out, void* cuda_stream);
+int ddcb200_session_push_host_packed10(ddcb200_session_t* s, const uint8_t* h_in, int64_t n_samples,
+                                       int64_t in_stride_bytes, ddcb200_c64* h_out, int64_t out_stride, int64_t* n_out);
 
 /* Pinned host memory helpers (the reference's prototype uses cuda.pagelocked_empty, ddc_host_gpu.py:45-58). */
 void* ddcb200_host_alloc(size_t bytes);

@@ -347,3 +347,29 @@ def test_sliced_staging_kernel_large_decimations(d, t, streams, tmp_path):
     emax, el2 = rel_err(y, ref)
     k = 4 if t > 256 else 1
     assert y.shape == ref.shape and emax <= k * TOL_MAX and el2 <= k * TOL_L2, (emax, el2)
+
+
+def test_streaming_packed_input(taps_dir):
+    """Packed 10-bit pushes (host and device) through a session equal one run() over the unpacked concatenation."""
+    from dc_sand_b200 import DDCStream
+
+    n = 200_000
+    xi = np.stack([synth.digitiser_stream(n, 90 + s) for s in range(2)])
+    packed = np.stack([synth.pack10(r) for r in xi])
+    ddc = _ddc(taps_dir, 16)
+    ref = np.stack([orc.ddc_reference(r.astype(np.float32), 100e6, ddc.ddc_filter_coeffs, 16, FS) for r in xi])
+    cuts = [0, 120, 4000, 70_004, 70_008, 150_000, n]           # multiples of 4 samples
+    with DDCStream(ddc, 100e6, n_streams=2, max_chunk=60_000, total_samples=n, packed=True) as st:
+        parts = []
+        for i, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+            piece = packed[:, a // 4 * 5: b // 4 * 5]
+            if i % 2 and b - a <= 60_000:
+                parts.append(st.push_tensor(torch.from_numpy(np.ascontiguousarray(piece)).cuda()).cpu().numpy())
+            else:
+                parts.append(st.push(piece))
+        assert st.position == n
+    y = np.concatenate(parts, axis=1)
+    emax, el2 = rel_err(y, ref)
+    assert y.shape == ref.shape and emax <= TOL_MAX and el2 <= TOL_L2, (y.shape, emax, el2)
+    with pytest.raises(ValueError):
+        DDCStream(ddc, 100e6, packed=True).push(np.zeros(7, np.uint8))
