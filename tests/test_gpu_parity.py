@@ -373,3 +373,55 @@ def test_streaming_packed_input(taps_dir):
     assert y.shape == ref.shape and emax <= TOL_MAX and el2 <= TOL_L2, (y.shape, emax, el2)
     with pytest.raises(ValueError):
         DDCStream(ddc, 100e6, packed=True).push(np.zeros(7, np.uint8))
+
+
+def test_headline_config_full_size(taps_dir):
+    """BASELINE configs[1] at full size: 1 stream x 2^28 float32 samples, T = 256, D = 16.  The input is generated in HBM
+    (ddcb200_cwg, digitiser model), windows of it are copied back and checked against the float64 windowed oracle, and two
+    size-independent properties are checked on the whole output: a time-chunked run reproduces the one-shot run, and the
+    stream shifted by one decimation step gives the output shifted by one sample (times the NCO step)."""
+    from dc_sand_b200 import cwg as mycwg
+
+    n, d = 1 << 28, 16
+    ddc = _ddc(taps_dir, d)
+    xt = mycwg.generate_carrier_wave_gpu(100.0, 103.3e6, FS, n, 40.0, False, seed=2026, digitise=True)
+    yt = ddc.run_tensor(xt, 100e6)
+    assert "fast_fir" in ddc.last_variant
+    m = ddc.out_len(n)
+    assert yt.shape == (m,) and m == 16777201
+    step = orc.phase_step_cycles(n, 100e6, FS)
+    rng = np.random.default_rng(1)
+    scale = float(yt.abs().max())
+    for s0 in [0, m - 512] + [int(v) for v in rng.integers(0, m - 512, size=10)]:
+        seg = xt[s0 * d: (s0 + 511) * d + 256].cpu().numpy()
+        ref = orc.ddc_windowed_f64(seg, s0, 512, step, ddc.ddc_filter_coeffs, d, x_base=s0 * d)
+        assert np.abs(yt[s0: s0 + 512].cpu().numpy() - ref).max() <= TOL_MAX * scale, s0
+    # chunked == one-shot (NCO phase continuity through sample_offset), here on the second quarter of the stream
+    q0 = (n // 4) // d * d
+    part = ddc.run_tensor(xt[q0: q0 + (1 << 26)], 100e6, sample_offset=q0, total_samples=n)
+    assert float((part - yt[q0 // d: q0 // d + part.shape[0]]).abs().max()) <= TOL_MAX * scale
+    # time shift by one decimation step: y'[m] = y[m + 1] up to the NCO phase origin
+    shifted = ddc.run_tensor(xt[d:], 100e6, sample_offset=d, total_samples=n)
+    assert float((shifted[: m - 1] - yt[1:]).abs().max()) <= TOL_MAX * scale
+
+
+def test_packed_config_full_size(taps_dir):
+    """BASELINE configs[2] at full size: 64 streams x 2^24 packed 10-bit samples through the fused-unpack kernel, against the
+    float32 path on the same samples (bit-exact unpack => same arithmetic up to the kernels' summation order)."""
+    n, s, d = 1 << 24, 64, 16
+    base = synth.digitiser_stream_fast(n, 77)
+    rows_p = torch.from_numpy(synth.pack10(base)).cuda()
+    rows_f = torch.from_numpy(base.astype(np.float32)).cuda()
+    # every stream is the base stream rotated by a different whole number of 64-sample groups (80 packed bytes)
+    xp = torch.stack([torch.roll(rows_p, -80 * 1000 * k) for k in range(s)])
+    ddc = _ddc(taps_dir, d)
+    yp = ddc.run_tensor(xp, 100e6, packed=True)
+    assert "packed10" in ddc.last_variant and yp.shape == (s, ddc.out_len(n))
+    scale = float(yp.abs().max())
+    for k in (0, 1, 31, 63):
+        yf = ddc.run_tensor(torch.roll(rows_f, -64 * 1000 * k), 100e6)
+        assert float((yp[k] - yf).abs().max()) <= TOL_MAX * scale, k
+    step = orc.phase_step_cycles(n, 100e6, FS)
+    x0 = base.astype(np.float32)
+    ref = orc.ddc_windowed_f64(x0, 12345, 512, step, ddc.ddc_filter_coeffs, d)
+    assert np.abs(yp[0, 12345: 12345 + 512].cpu().numpy() - ref).max() <= TOL_MAX * scale
