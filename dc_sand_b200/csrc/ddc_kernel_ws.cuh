@@ -19,13 +19,15 @@ namespace ddck {
 
 template <int D, int JT>
 struct WSCfg {
-    static_assert(D == 32 || D == 64, "sliced staging is for D = 32, 64");
+    static_assert(D == 4 || D == 8 || D == 32 || D == 64, "tensor-staged kernel: D = 32, 64 (sliced) and D = 4, 8 (whole blocks)");
     static_assert(JT % 2 == 0 && JT <= 32, "tap blocks: even, at most 32 (halo of four thread-rows)");
-    static constexpr int LPQ = D / 16;             // slices per chunk
-    static constexpr int DB = 16;                  // floats of one block inside a slice
+    // D = 4 / 8 use the same staging with ONE slice that holds the whole D-sample block: thread-rows of 8 blocks (32 / 64
+    // samples) give R = 8 outputs per thread, which the 1-D kernels (128-sample rows) cannot offer at these decimations.
+    static constexpr int LPQ = D < 16 ? 1 : D / 16;   // slices per chunk
+    static constexpr int DB = D < 16 ? D : 16;        // floats of one block inside a slice
     static constexpr int R = 8;                    // outputs (= blocks) per thread-row
-    static constexpr int ROW = R * DB;             // floats of one thread-row inside a slice (128)
-    static constexpr int V = 4;                    // phase groups per slice
+    static constexpr int ROW = R * DB;             // floats of one thread-row inside a slice
+    static constexpr int V = DB / 4;               // phase groups per slice
     static constexpr int JP = JT < 16 ? JT : 16;   // tap blocks per pass
     static constexpr int NJG = JT / JP;            // passes per slice
     static_assert(JT % JP == 0, "long filters are padded to a multiple of 16 tap blocks");
@@ -39,14 +41,19 @@ struct WSCfg {
     // thread-row L, so the eight lanes of a quarter warp read eight consecutive lines at the same logical unit and hit
     // eight distinct bank groups.  Tiles are 512-byte aligned (2304 bytes of data in a 2560-byte pitch).
     // (The 128-byte swizzle pads every 64-byte box row to a 128-byte line: tools/microbench/tma_swizzle_probe.cu.)
+    // With 32-byte lines (D = 8) the 32-byte swizzle does the same job (unit ^= (row / 4) % 2, bits 5-6 = row % 4); 16-byte
+    // lines (D = 4) are conflict-free as they are.
     static constexpr int SLOT_ROWS = 36;           // 32 + up to 4 halo rows
-    static constexpr int TILE_BYTES = 2560;        // per block index: 36 x 64 B, rounded up to a multiple of 512
-    static constexpr int SLOT_BYTES = R * TILE_BYTES;          // 20 KB
-    static constexpr int TX_BYTES = R * SLOT_ROWS * 64;        // bytes landed per slot: 18 KB
+    static constexpr int LINE_BYTES = DB * 4;      // 64 / 32 / 16
+    static constexpr int TILE_BYTES = 40 * LINE_BYTES;         // per block index: 36 lines, pitch a multiple of the swizzle period
+    static constexpr int SLOT_BYTES = R * TILE_BYTES;          // 20 / 10 / 5 KB
+    static constexpr int TX_BYTES = R * SLOT_ROWS * LINE_BYTES;   // bytes landed per slot
     static constexpr int HDR_BYTES = 1024;
     static constexpr int NGROUPS = 8, NWARPS = 8, NPROD = 2;
-    static constexpr int NSLOT = (227 * 1024 - HDR_BYTES - 1024) / SLOT_BYTES;   // 11
+    static constexpr int NSLOT_MAX = (227 * 1024 - HDR_BYTES - 1024) / SLOT_BYTES;
+    static constexpr int NSLOT = NSLOT_MAX > 16 ? 16 : NSLOT_MAX;   // 11 at D >= 32
     static_assert(NSLOT >= NGROUPS + 2 && NSLOT <= 16, "ring size");
+    __host__ __device__ static constexpr int swz(int row) { return DB == 16 ? ((row >> 1) & 3) : (DB == 8 ? ((row >> 2) & 1) : 0); }
     static constexpr int CHUNK_ROWS = 32;
     static constexpr int CHUNK_OUT = CHUNK_ROWS * R;       // 256 outputs
     static constexpr int CHUNK_BLOCKS = CHUNK_ROWS * R;    // 256 D-sample blocks
@@ -138,13 +145,13 @@ ddc_fused_ws_kernel(const __grid_constant__ RunParams p, const __grid_constant__
         const int grp = warp;
         const int g = lane;   // lane L owns thread-row L of the chunk (see WSCfg)
         // window of a pass: blocks 0 .. NW-1 of thread-rows grow, grow+1, ...; phase group pgv.  Block blk of row `row` lives in
-        // tile blk at line `row`, logical 16-byte unit pgv, physical unit pgv ^ ((row / 2) % 4).
+        // tile blk at line `row`, logical 16-byte unit pgv, physical unit pgv ^ swz(row).
         auto load_window = [&](float4(&w)[NW], const unsigned char* sb, int grow, int pgv) {
             int a[C::WROWS];
 #pragma unroll
             for (int h = 0; h < C::WROWS; ++h) {
                 const int row = grow + h;
-                a[h] = row * 64 + ((pgv ^ ((row >> 1) & 3)) << 4);
+                a[h] = row * C::LINE_BYTES + ((pgv ^ C::swz(row)) << 4);
             }
 #pragma unroll
             for (int b = 0; b < NW; ++b) w[b] = *reinterpret_cast<const float4*>(sb + a[b / R] + (b % R) * C::TILE_BYTES);
@@ -212,6 +219,12 @@ ddc_fused_ws_kernel(const __grid_constant__ RunParams p, const __grid_constant__
             {
                 int grow = g;
                 int pgi = 1;
+                if (C::V == 1) {   // one phase group per tap group: the next pass already belongs to the next tap group
+                    pgi = 0;
+                    pgv = 0;
+                    grow += JP / R;
+                    tp += 3 * (JP / 2) * (D / 2) - 2 * C::V;
+                }
 #pragma unroll 1
                 for (int pass = 1; pass < NJG * C::V; ++pass) {
                     asm volatile("" : "+r"(pgv), "+r"(grow));   // per-thread copies, hidden from the uniform induction variables

@@ -425,3 +425,21 @@ def test_packed_config_full_size(taps_dir):
     x0 = base.astype(np.float32)
     ref = orc.ddc_windowed_f64(x0, 12345, 512, step, ddc.ddc_filter_coeffs, d)
     assert np.abs(yp[0, 12345: 12345 + 512].cpu().numpy() - ref).max() <= TOL_MAX * scale
+
+
+@pytest.mark.parametrize("d,t", [(4, 64), (4, 128), (8, 128), (8, 40)])
+def test_tensor_staged_kernel_small_decimations(d, t, tmp_path):
+    """D = 4 / 8 through the tensor-staged fast-FIR kernel (whole blocks, 32-byte swizzle / plain 16-byte lines), 2 streams,
+    ragged length."""
+    from scipy import signal
+
+    n = 8 * d * 3000 + 3 * d + 4
+    tp = signal.firwin(t, 0.8 / d)
+    ddc = DigitalDownConverter(d, FS, _custom_taps(tmp_path, tp))
+    ddc.set_option("variant", 11)
+    xs = np.stack([synth.digitiser_stream(n, 700 + d + s) for s in range(2)]).astype(np.float32)
+    y = ddc.run_tensor(torch.from_numpy(xs).cuda(), 100e6).cpu().numpy()
+    assert "tensor_staged" in ddc.last_variant, ddc.last_variant
+    ref = np.stack([orc.ddc_reference(r, 100e6, tp, d, FS) for r in xs])
+    emax, el2 = rel_err(y, ref)
+    assert y.shape == ref.shape and emax <= TOL_MAX and el2 <= TOL_L2, (emax, el2)
