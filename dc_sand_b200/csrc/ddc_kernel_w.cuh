@@ -1082,6 +1082,7 @@ ddc_fused_w10s_kernel(const __grid_constant__ RunParams p, const __grid_constant
             mbar_wait(&raw_full[rs], (uint32_t)(k / NR) & 1u);
             if (k >= NF)
                 while (f_done[fs] != k - NF) {}     // the FIR warp has finished the chunk that lived in this float slot
+            __threadfence_block();
             __syncwarp();
             const uint32_t* rw = reinterpret_cast<const uint32_t*>(rbuf + (size_t)rs * RAWB);
             float* sbuf = fbuf + (size_t)fs * C::SLOT_FLOATS;
@@ -1151,6 +1152,7 @@ ddc_fused_w10s_kernel(const __grid_constant__ RunParams p, const __grid_constant
                 while (f_ready[fs] != k) {}
                 if (p.dbg) t_wait += clock64() - tw0;
             }
+            __threadfence_block();   // acquire: the unpackers' stores to the slot are visible before my loads
             __syncwarp();
             const float* sbuf = fbuf + (size_t)fs * C::SLOT_FLOATS;
 #pragma unroll

@@ -443,3 +443,20 @@ def test_tensor_staged_kernel_small_decimations(d, t, tmp_path):
     ref = np.stack([orc.ddc_reference(r, 100e6, tp, d, FS) for r in xs])
     emax, el2 = rel_err(y, ref)
     assert y.shape == ref.shape and emax <= TOL_MAX and el2 <= TOL_L2, (emax, el2)
+
+
+def test_warp_specialised_packed_kernel(taps_dir):
+    """Option variant=10: unpack warps feeding a float ring, FIR warps consuming it (sequence-word hand-over in shared memory).
+    Many chunks per CTA so that every ring slot is reused several times; result against the float32 path."""
+    n = 1 << 22
+    base = synth.digitiser_stream_fast(n, 21)
+    ddc = _ddc(taps_dir, 16)
+    xp = torch.from_numpy(np.stack([synth.pack10(np.roll(base, 64 * k)) for k in range(12)])).cuda()
+    ddc.set_option("variant", 10)
+    y = ddc.run_tensor(xp, 100e6, packed=True)
+    assert "split" in ddc.last_variant, ddc.last_variant
+    ddc.set_option("variant", 0)
+    scale = float(y.abs().max())
+    for k in (0, 5, 11):
+        yf = ddc.run_tensor(torch.from_numpy(np.roll(base, 64 * k).astype(np.float32)).cuda(), 100e6)
+        assert float((y[k] - yf).abs().max()) <= TOL_MAX * scale, k
