@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the fused digital down-converter (BASELINE.json: "DDC input Gsamples/s and % of HBM roofline").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c5|sweep]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c5]     (sweep: tools/sweep.py)
 
 One "step" = one pass of the hot path (NCO mix -> FIR -> decimate) over one batch of synthetic digitiser samples.
   N = 1  : BASELINE configs[1]  "single L-band stream (1712 MSPS), 2^28 samples, 256 taps, decimation 16".
