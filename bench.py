@@ -115,6 +115,45 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def bind_to_gpu_numa(index: int):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned host buffers are allocated
+    (first touch puts them on that node).  With one rank per GPU this keeps every rank's H2D / D2H traffic on its own
+    memory controller; without it the end-to-end leg of an 8-rank run shares one node's bandwidth.  Best effort."""
+    try:
+        import torch
+
+        bus = torch.cuda.get_device_properties(index).pci_bus_id   # torch >= 2.x: "0000:1B:00.0"-like
+    except Exception:
+        bus = None
+    try:
+        if bus is None:
+            import pynvml
+
+            pynvml.nvmlInit()
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def make_input(n_streams: int, n: int, rank: int, packed: bool):
     """Synthetic tone + noise, 10-bit quantised. Large arrays reuse a 2^22-sample block per stream (rolled)."""
     from dc_sand_b200 import synth
@@ -247,6 +286,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = bind_to_gpu_numa(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -434,6 +474,7 @@ def run_ours(args):
             },
             "gpu_launches": int(launches),
             "final_gather_ms_untimed": gather_ms,
+            "numa_node_rank0": numa_node,
             "clocks": clk.summary(),
         }
         if args.gpus == 1 and not args.no_cpu:
