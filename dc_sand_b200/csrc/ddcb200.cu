@@ -12,6 +12,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ddc_kernels.cuh"
@@ -90,6 +91,13 @@ struct ddcb200 {
     std::vector<float2> wt_cache;
     double wt_step = 0.0;
     int wt_jt = 0, wt_d = 0, wt_nest = 0;
+    // pinned staging for pageable host input (see staged_h2d)
+    static constexpr int kStage = 2;
+    static constexpr size_t kStageBytes = 8u << 20;
+    void* h_stage[kStage] = {};
+    cudaEvent_t ev_stage[kStage] = {};
+    int stage_pos = 0;
+    int copy_threads = 4;
     std::vector<float2> wq_cache;   // same for the small-decimation kernel
     double wq_step = 0.0;
     int wq_jt = 0, wq_nq = 0;
@@ -869,6 +877,51 @@ int ensure_chunks(ddcb200* h, size_t in_bytes, size_t out_elems) {
     return DDCB200_OK;
 }
 
+// H2D copy from PAGEABLE host memory: cudaMemcpyAsync would fall back to the driver's single-threaded staging (about
+// 12 GB/s).  Instead the bytes go through two pinned 8 MB staging buffers filled by a few host threads (memcpy is
+// memory-bandwidth bound, one core does not saturate it) while the previous buffer is in flight on the copy engine.
+bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+int staged_h2d(ddcb200* h, void* d_dst, const void* h_src, size_t bytes, cudaStream_t st) {
+    for (int i = 0; i < ddcb200::kStage; ++i) {
+        if (!h->h_stage[i]) CUDA_TRY(cudaMallocHost(&h->h_stage[i], ddcb200::kStageBytes));
+        if (!h->ev_stage[i]) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_stage[i], cudaEventDisableTiming));
+    }
+    const int nt = std::max(1, std::min(h->copy_threads, 16));
+    size_t done = 0;
+    while (done < bytes) {
+        const size_t n = std::min(bytes - done, ddcb200::kStageBytes);
+        const int b = h->stage_pos;
+        h->stage_pos = (h->stage_pos + 1) % ddcb200::kStage;
+        CUDA_TRY(cudaEventSynchronize(h->ev_stage[b]));   // the copy engine has drained this staging buffer
+        char* dst = static_cast<char*>(h->h_stage[b]);
+        const char* src = static_cast<const char*>(h_src) + done;
+        if (nt == 1 || n < (1u << 20)) {
+            std::memcpy(dst, src, n);
+        } else {
+            const size_t per = ((n + nt - 1) / nt + 63) & ~(size_t)63;
+            std::vector<std::thread> th;
+            for (int t = 1; t < nt; ++t) {
+                const size_t o = per * t;
+                if (o < n) th.emplace_back([=] { std::memcpy(dst + o, src + o, std::min(per, n - o)); });
+            }
+            std::memcpy(dst, src, std::min(per, n));
+            for (auto& t : th) t.join();
+        }
+        CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(d_dst) + done, dst, n, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaEventRecord(h->ev_stage[b], st));
+        done += n;
+    }
+    return DDCB200_OK;
+}
+
 // Host path: every stream is cut into time chunks of `chunk_samples` (+ T-D halo); chunk c of all streams goes
 // H2D on copy_in, through the fused kernel on `stream`, and D2H on copy_out, three buffers deep.
 int run_host(ddcb200* h, const void* h_in, bool packed, int64_t n_samples, int64_t n_streams, int64_t in_stride,
@@ -891,6 +944,7 @@ int run_host(ddcb200* h, const void* h_in, bool packed, int64_t n_samples, int64
     const size_t in_row_bytes = (size_t)in_chunk_samples / in_elem_den * in_elem_bytes_num;
     int rc = ensure_chunks(h, in_row_bytes * (size_t)n_streams + 64, (size_t)m_chunk * (size_t)n_streams);
     if (rc) return rc;
+    const bool pageable_in = h->copy_threads > 0 && is_pageable(h_in);
 
     for (int64_t c = 0; c < n_chunks; ++c) {
         const int b = (int)(c % ddcb200::kBufs);
@@ -904,8 +958,13 @@ int run_host(ddcb200* h, const void* h_in, bool packed, int64_t n_samples, int64
         const size_t src_pitch = packed ? (size_t)in_stride : (size_t)in_stride * 4;
         // buffer b is free once the D2H of chunk c - kBufs finished (ev_out) -- wait on the copy-in stream
         if (c >= ddcb200::kBufs) CUDA_TRY(cudaStreamWaitEvent(h->copy_in, h->ev_k[b], 0));
-        CUDA_TRY(cudaMemcpy2DAsync(h->d_chunk_in[b], in_row_bytes, reinterpret_cast<const char*>(h_in) + src_off, src_pitch,
-                                   row_bytes, (size_t)n_streams, cudaMemcpyHostToDevice, h->copy_in));
+        if (n_streams == 1 && pageable_in && row_bytes >= (4u << 20)) {
+            rc = staged_h2d(h, h->d_chunk_in[b], reinterpret_cast<const char*>(h_in) + src_off, row_bytes, h->copy_in);
+            if (rc) return rc;
+        } else {
+            CUDA_TRY(cudaMemcpy2DAsync(h->d_chunk_in[b], in_row_bytes, reinterpret_cast<const char*>(h_in) + src_off, src_pitch,
+                                       row_bytes, (size_t)n_streams, cudaMemcpyHostToDevice, h->copy_in));
+        }
         CUDA_TRY(cudaEventRecord(h->ev_in[b], h->copy_in));
         CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
         if (c >= ddcb200::kBufs) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_out[b], 0));
@@ -1000,6 +1059,10 @@ void ddcb200_destroy(ddcb200_t* h) {
         if (h->d_ctaps[i]) cudaFree(h->d_ctaps[i]);
         if (h->h_ctaps[i]) cudaFreeHost(h->h_ctaps[i]);
         if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
+    }
+    for (int i = 0; i < ddcb200::kStage; ++i) {
+        if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]);
+        if (h->ev_stage[i]) cudaEventDestroy(h->ev_stage[i]);
     }
     for (int i = 0; i < ddcb200::kBufs; ++i) {
         if (h->d_chunk_in[i]) cudaFree(h->d_chunk_in[i]);
@@ -1230,6 +1293,11 @@ int ddcb200_set_option(ddcb200_t* h, const char* key, int64_t value) {
     }
     if (!strcmp(key, "debug_mode")) {
         h->debug_mode = (int)value;
+        return DDCB200_OK;
+    }
+    if (!strcmp(key, "copy_threads")) {   // host threads of the pageable-input staging path (0 = let the driver stage)
+        if (value < 0 || value > 16) return fail(DDCB200_EINVAL, "copy_threads must be 0 .. 16");
+        h->copy_threads = (int)value;
         return DDCB200_OK;
     }
     if (!strcmp(key, "chunk_samples")) {
