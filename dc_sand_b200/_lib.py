@@ -27,6 +27,7 @@ SIGNATURES = {
     "ddcb200_decimate_c64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "ddcb200_run_host_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int64,
                                        C.c_void_p, C.c_int64]),
+    "ddcb200_run_host_f32_c128": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int64, C.c_void_p]),
     "ddcb200_run_host_packed10": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double,
                                             C.c_int64, C.c_void_p, C.c_int64]),
     "ddcb200_cwg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_double,

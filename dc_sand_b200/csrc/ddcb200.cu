@@ -98,6 +98,8 @@ struct ddcb200 {
     cudaEvent_t ev_stage[kStage] = {};
     int stage_pos = 0;
     int copy_threads = 4;
+    ddcb200_c64* h_ostage[kBufs] = {};   // pinned landing buffers for the complex128 host path (one per chunk buffer)
+    size_t ostage_cap = 0;
     std::vector<float2> wq_cache;   // same for the small-decimation kernel
     double wq_step = 0.0;
     int wq_jt = 0, wq_nq = 0;
@@ -922,10 +924,35 @@ int staged_h2d(ddcb200* h, void* d_dst, const void* h_src, size_t bytes, cudaStr
     return DDCB200_OK;
 }
 
+// complex64 -> complex128 on a few host threads, straight into the caller's (usually fresh, untouched) array: the page
+// faults of the first touch are spread over the threads as well
+void widen_c64_to_c128(const ddcb200_c64* src, double* dst, size_t n, int nt) {
+    auto work = [=](size_t a, size_t b) {
+        for (size_t i = a; i < b; ++i) {
+            dst[2 * i] = (double)src[i].re;
+            dst[2 * i + 1] = (double)src[i].im;
+        }
+    };
+    nt = std::max(1, std::min(nt, 16));
+    if (nt == 1 || n < (1u << 16)) {
+        work(0, n);
+        return;
+    }
+    const size_t per = (n + nt - 1) / nt;
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t)
+        if (per * t < n) th.emplace_back(work, per * t, std::min(n, per * (t + 1)));
+    work(0, std::min(per, n));
+    for (auto& t : th) t.join();
+}
+
 // Host path: every stream is cut into time chunks of `chunk_samples` (+ T-D halo); chunk c of all streams goes
 // H2D on copy_in, through the fused kernel on `stream`, and D2H on copy_out, three buffers deep.
 int run_host(ddcb200* h, const void* h_in, bool packed, int64_t n_samples, int64_t n_streams, int64_t in_stride,
-             double step, int64_t sample_offset, ddcb200_c64* h_out, int64_t out_stride) {
+             double step, int64_t sample_offset, ddcb200_c64* h_out, int64_t out_stride, double* h_out128 = nullptr) {
+    // h_out128 (one stream only): the result is delivered as complex128 (the reference's dtype) -- every chunk lands in a
+    // pinned buffer and is widened on the host threads while the next chunk is in flight
+    if (h_out128) h_out = reinterpret_cast<ddcb200_c64*>(h_out128);   // only for the null check below
     const int T = (int)h->taps.size();
     const int D = h->decim;
     if (!h_in || !h_out) return fail(DDCB200_EINVAL, "null host pointer");
@@ -945,6 +972,26 @@ int run_host(ddcb200* h, const void* h_in, bool packed, int64_t n_samples, int64
     int rc = ensure_chunks(h, in_row_bytes * (size_t)n_streams + 64, (size_t)m_chunk * (size_t)n_streams);
     if (rc) return rc;
     const bool pageable_in = h->copy_threads > 0 && is_pageable(h_in);
+    if (h_out128) {
+        if (n_streams != 1) return fail(DDCB200_EINVAL, "complex128 host output is for one stream per call");
+        if ((size_t)m_chunk > h->ostage_cap) {
+            for (int i = 0; i < ddcb200::kBufs; ++i) {
+                if (h->h_ostage[i]) cudaFreeHost(h->h_ostage[i]);
+                h->h_ostage[i] = nullptr;
+                CUDA_TRY(cudaMallocHost(&h->h_ostage[i], (size_t)m_chunk * sizeof(ddcb200_c64)));
+            }
+            h->ostage_cap = (size_t)m_chunk;
+        }
+    }
+    int64_t pend_m0 = -1, pend_mc = 0;   // chunk whose outputs still have to be widened
+    int pend_b = 0;
+    auto flush_pending = [&]() -> int {
+        if (pend_m0 < 0) return DDCB200_OK;
+        CUDA_TRY(cudaEventSynchronize(h->ev_out[pend_b]));
+        widen_c64_to_c128(h->h_ostage[pend_b], h_out128 + 2 * pend_m0, (size_t)pend_mc, std::max(1, h->copy_threads));
+        pend_m0 = -1;
+        return DDCB200_OK;
+    };
 
     for (int64_t c = 0; c < n_chunks; ++c) {
         const int b = (int)(c % ddcb200::kBufs);
@@ -958,7 +1005,7 @@ int run_host(ddcb200* h, const void* h_in, bool packed, int64_t n_samples, int64
         const size_t src_pitch = packed ? (size_t)in_stride : (size_t)in_stride * 4;
         // buffer b is free once the D2H of chunk c - kBufs finished (ev_out) -- wait on the copy-in stream
         if (c >= ddcb200::kBufs) CUDA_TRY(cudaStreamWaitEvent(h->copy_in, h->ev_k[b], 0));
-        if (n_streams == 1 && pageable_in && row_bytes >= (4u << 20)) {
+        if (n_streams == 1 && pageable_in && row_bytes >= (16u << 20)) {   // below that the thread start-up costs more than it saves
             rc = staged_h2d(h, h->d_chunk_in[b], reinterpret_cast<const char*>(h_in) + src_off, row_bytes, h->copy_in);
             if (rc) return rc;
         } else {
@@ -975,11 +1022,26 @@ int run_host(ddcb200* h, const void* h_in, bool packed, int64_t n_samples, int64
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(h->ev_k[b], h->stream));
         CUDA_TRY(cudaStreamWaitEvent(h->copy_out, h->ev_k[b], 0));
-        CUDA_TRY(cudaMemcpy2DAsync(h_out + m0, (size_t)out_stride * sizeof(ddcb200_c64), h->d_chunk_out[b],
-                                   (size_t)m_chunk * sizeof(ddcb200_c64), (size_t)mc * sizeof(ddcb200_c64), (size_t)n_streams,
-                                   cudaMemcpyDeviceToHost, h->copy_out));
-        CUDA_TRY(cudaEventRecord(h->ev_out[b], h->copy_out));
+        if (h_out128) {
+            // the landing buffer of this chunk buffer was widened before its kernel was queued (kBufs = 3 chunks ago at the
+            // latest: flush_pending runs one chunk behind)
+            CUDA_TRY(cudaMemcpyAsync(h->h_ostage[b], h->d_chunk_out[b], (size_t)mc * sizeof(ddcb200_c64), cudaMemcpyDeviceToHost,
+                                     h->copy_out));
+            CUDA_TRY(cudaEventRecord(h->ev_out[b], h->copy_out));
+            rc = flush_pending();   // the previous chunk, while this one is in flight
+            if (rc) return rc;
+            pend_m0 = m0;
+            pend_mc = mc;
+            pend_b = b;
+        } else {
+            CUDA_TRY(cudaMemcpy2DAsync(h_out + m0, (size_t)out_stride * sizeof(ddcb200_c64), h->d_chunk_out[b],
+                                       (size_t)m_chunk * sizeof(ddcb200_c64), (size_t)mc * sizeof(ddcb200_c64), (size_t)n_streams,
+                                       cudaMemcpyDeviceToHost, h->copy_out));
+            CUDA_TRY(cudaEventRecord(h->ev_out[b], h->copy_out));
+        }
     }
+    rc = flush_pending();
+    if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(h->copy_out));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->copy_in));
@@ -1064,6 +1126,8 @@ void ddcb200_destroy(ddcb200_t* h) {
         if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]);
         if (h->ev_stage[i]) cudaEventDestroy(h->ev_stage[i]);
     }
+    for (int i = 0; i < ddcb200::kBufs; ++i)
+        if (h->h_ostage[i]) cudaFreeHost(h->h_ostage[i]);
     for (int i = 0; i < ddcb200::kBufs; ++i) {
         if (h->d_chunk_in[i]) cudaFree(h->d_chunk_in[i]);
         if (h->d_chunk_out[i]) cudaFree(h->d_chunk_out[i]);
@@ -1229,6 +1293,23 @@ int ddcb200_run_host_f32(ddcb200_t* h, const float* h_in, int64_t n_samples, int
         return DDCB200_OK;
     }
     return run_host(h, h_in, false, n_samples, n_streams, in_stride, step, sample_offset, h_out, out_stride);
+}
+
+int ddcb200_run_host_f32_c128(ddcb200_t* h, const float* h_in, int64_t n_samples, double step, int64_t sample_offset,
+                              double* h_out) {
+    if (!h) return fail(DDCB200_EINVAL, "null handle");
+    if (!h_in || !h_out) return fail(DDCB200_EINVAL, "null host pointer");
+    DeviceGuard g(h->device);
+    const int T = (int)h->taps.size();
+    if (n_samples > 0 && n_samples < T) {   // the scipy operand swap: few outputs, go through the complex64 entry point
+        const int64_t m = ddcb200_out_len(n_samples, T, h->decim);
+        std::vector<ddcb200_c64> tmp((size_t)m);
+        int rc = ddcb200_run_host_f32(h, h_in, n_samples, 1, n_samples, step, sample_offset, tmp.data(), m);
+        if (rc) return rc;
+        widen_c64_to_c128(tmp.data(), h_out, (size_t)m, 1);
+        return DDCB200_OK;
+    }
+    return run_host(h, h_in, false, n_samples, 1, n_samples, step, sample_offset, nullptr, 0, h_out);
 }
 
 int ddcb200_run_host_packed10(ddcb200_t* h, const uint8_t* h_in, int64_t n_samples, int64_t n_streams,

@@ -135,12 +135,14 @@ class DigitalDownConverter:
         h = self._get_handle()
         lib = _lib.load()
         m = self.out_len(n)
-        out = np.empty(m, dtype=np.complex64)
+        # complex128 like the reference; widened from the device's complex64 inside the library (on host threads, chunk by
+        # chunk under the transfers) rather than by a second pass here
+        out = np.empty(m, dtype=np.complex128)
         _lib.check(
-            lib.ddcb200_run_host_f32(h, x.ctypes.data, n, 1, n, step, int(sample_offset), out.ctypes.data, m),
-            "ddcb200_run_host_f32",
+            lib.ddcb200_run_host_f32_c128(h, x.ctypes.data, n, step, int(sample_offset), out.ctypes.data),
+            "ddcb200_run_host_f32_c128",
         )
-        return out.astype(np.complex128)
+        return out
 
     def run_batch(self, input_data: np.ndarray, center_freq: float, sample_offset: int = 0,
                   total_samples: int | None = None, out: np.ndarray | None = None) -> np.ndarray:

@@ -124,6 +124,11 @@ int ddcb200_cwg(ddcb200_t* handle, void* d_out, int64_t num_samples, int64_t n_s
 int ddcb200_run_host_f32(ddcb200_t* handle, const float* h_in, int64_t n_samples, int64_t n_streams,
                          int64_t in_stride, double phase_step_cycles, int64_t sample_offset,
                          ddcb200_c64* h_out, int64_t out_stride);
+/* One stream, result as complex128 (interleaved re, im float64) -- the dtype DigitalDownConverter.run returns
+ * (ddc.py:98,119: scipy.signal.convolve of a complex64 array with float64 taps).  The arithmetic is the complex64 path's;
+ * the widening happens on host threads straight into the caller's array while the next chunk is in flight. */
+int ddcb200_run_host_f32_c128(ddcb200_t* handle, const float* h_in, int64_t n_samples, double phase_step_cycles,
+                              int64_t sample_offset, double* h_out);
 int ddcb200_run_host_packed10(ddcb200_t* handle, const uint8_t* h_in, int64_t n_samples, int64_t n_streams,
                               int64_t in_stride_bytes, double phase_step_cycles, int64_t sample_offset,
                               ddcb200_c64* h_out, int64_t out_stride);

@@ -460,3 +460,23 @@ def test_warp_specialised_packed_kernel(taps_dir):
     for k in (0, 5, 11):
         yf = ddc.run_tensor(torch.from_numpy(np.roll(base, 64 * k).astype(np.float32)).cuda(), 100e6)
         assert float((y[k] - yf).abs().max()) <= TOL_MAX * scale, k
+
+
+def test_run_on_large_pageable_array(taps_dir):
+    """run() on a 32 MB pageable NumPy array: multi-threaded pinned staging of the input and complex128 widening of the output
+    on host threads (ddcb200_run_host_f32_c128); same result as the device-tensor path, dtype of the reference."""
+    n = (1 << 23) + 12345
+    x = synth.digitiser_stream_fast(n, 31).astype(np.float32)
+    ddc = _ddc(taps_dir, 16)
+    ddc.set_option("chunk_samples", 1 << 22)          # several time chunks, so the one-chunk-behind widening is exercised
+    y = ddc.run(x, 100e6)
+    assert y.dtype == np.complex128 and y.shape == (ddc.out_len(n),)
+    yd = ddc.run_tensor(torch.from_numpy(x).cuda(), 100e6).cpu().numpy()
+    scale = np.abs(yd).max()
+    assert np.abs(y - yd).max() <= TOL_MAX * scale
+    step = orc.phase_step_cycles(n, 100e6, FS)
+    for s0 in (0, 262_000, len(y) - 512):
+        ref = orc.ddc_windowed_f64(x, s0, 512, step, ddc.ddc_filter_coeffs, 16)
+        assert np.abs(y[s0:s0 + 512] - ref).max() <= TOL_MAX * scale, s0
+    ddc.set_option("copy_threads", 0)                  # the driver-staged path gives the same values
+    assert np.array_equal(ddc.run(x, 100e6), y)
