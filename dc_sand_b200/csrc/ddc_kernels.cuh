@@ -74,6 +74,21 @@ __global__ void unpack10_kernel(const uint8_t* __restrict__ in, long long n_grou
     }
 }
 
+// unpack stage for [streams][5 N / 4] packed rows -> [streams][pitch] float32 rows: the first half of the two-launch path that
+// serves packed input for tap / decimation combinations without a fused-unpack kernel
+__global__ void unpack10_rows_kernel(const uint8_t* __restrict__ in, long long in_stride_bytes, long long n_groups,
+                                     float* __restrict__ out, long long out_stride) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const uint8_t* b = in + (long long)blockIdx.y * in_stride_bytes + g * 5;
+    const uint32_t b0 = b[0];
+    const uint32_t lo = ((uint32_t)b[1] << 24) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 8) | (uint32_t)b[4];
+    int v[4];
+    unpack10_word(b0, lo, v);
+    *reinterpret_cast<float4*>(out + (long long)blockIdx.y * out_stride + g * 4) =
+        make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+}
+
 // Stage kernels: the reference exposes its three stages as separate methods (ddc.py:51-66, 85-100, 102-119).  The fused
 // kernels above are what run() uses; these exist so that the stage methods of the drop-in class also execute on the GPU.
 __global__ void mix_kernel(const float* __restrict__ x, const float2* __restrict__ cw, float2* __restrict__ out, long long n) {

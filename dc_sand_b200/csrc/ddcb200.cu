@@ -98,6 +98,8 @@ struct ddcb200 {
     cudaEvent_t ev_stage[kStage] = {};
     int stage_pos = 0;
     int copy_threads = 4;
+    float* d_unpack_ws = nullptr;          // float32 workspace of the two-launch packed path (unpack, then a float32 kernel)
+    size_t unpack_ws_cap = 0;
     ddcb200_c64* h_ostage[kBufs] = {};   // pinned landing buffers for the complex128 host path (one per chunk buffer)
     size_t ostage_cap = 0;
     std::vector<float2> wq_cache;   // same for the small-decimation kernel
@@ -710,6 +712,32 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         }
     }
 
+    // ---- packed input without a fused-unpack kernel for this (T, D): unpack into a float32 workspace, then the float32 path --
+    if (packed && h->force_variant != 1) {
+        const long long pitch = (n_samples + 3) / 4 * 4;
+        const size_t need = (size_t)pitch * (size_t)n_streams;
+        if (need > h->unpack_ws_cap) {
+            CUDA_TRY(cudaStreamSynchronize(st));   // a previous launch may still read the old workspace
+            if (h->d_unpack_ws) cudaFree(h->d_unpack_ws);
+            h->d_unpack_ws = nullptr;
+            h->unpack_ws_cap = 0;
+            if (cudaMalloc(&h->d_unpack_ws, need * sizeof(float)) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(DDCB200_ENOMEM, "packed input: cannot allocate a %zu-byte unpack workspace", need * sizeof(float));
+            }
+            h->unpack_ws_cap = need;
+        }
+        const long long groups = n_samples / 4;
+        dim3 grid((unsigned)((groups + 255) / 256), (unsigned)n_streams);
+        unpack10_rows_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(d_in), in_stride, groups, h->d_unpack_ws, pitch);
+        CUDA_TRY(cudaGetLastError());
+        h->launches++;
+        int rc2 = run_device(h, h->d_unpack_ws, false, n_samples, n_streams, pitch, step, sample_offset, d_out, out_stride, st, m_limit);
+        if (rc2) return rc2;
+        h->last_variant = "unpack10+" + h->last_variant;
+        return DDCB200_OK;
+    }
+
     // ---- large decimations (D = 32, 64): sliced staging (ddc_kernel_ws.cuh), fast FIR with R = 8 outputs per thread ----------
     // Auto: where the direct form is FP32-bound (4 T / D flop per sample against 4 + 8 / D bytes at the measured ridge of
     // 11.4 flop/B); HBM-bound cells stay on the phase-major kernel, which over-fetches nothing.  Option "variant" 11 forces it.
@@ -1130,6 +1158,7 @@ void ddcb200_destroy(ddcb200_t* h) {
     }
     for (int i = 0; i < ddcb200::kBufs; ++i)
         if (h->h_ostage[i]) cudaFreeHost(h->h_ostage[i]);
+    if (h->d_unpack_ws) cudaFree(h->d_unpack_ws);
     for (int i = 0; i < ddcb200::kBufs; ++i) {
         if (h->d_chunk_in[i]) cudaFree(h->d_chunk_in[i]);
         if (h->d_chunk_out[i]) cudaFree(h->d_chunk_out[i]);

@@ -480,3 +480,24 @@ def test_run_on_large_pageable_array(taps_dir):
         assert np.abs(y[s0:s0 + 512] - ref).max() <= TOL_MAX * scale, s0
     ddc.set_option("copy_threads", 0)                  # the driver-staged path gives the same values
     assert np.array_equal(ddc.run(x, 100e6), y)
+
+
+@pytest.mark.parametrize("d,t", [(16, 1024), (8, 256), (32, 512), (16, 40)])
+def test_packed_input_any_filter(d, t, tmp_path):
+    """Packed input for (T, D) without a fused-unpack kernel goes through the unpack stage into a workspace and then the
+    float32 kernel of that cell; same result as unpacking on the host first."""
+    from scipy import signal
+
+    n = 400_000
+    tp = signal.firwin(t, 0.8 / d)
+    xi = np.stack([synth.digitiser_stream(n, 40 + d + s) for s in range(2)])
+    ddc = DigitalDownConverter(d, FS, _custom_taps(tmp_path, tp))
+    yp = ddc.run_tensor(torch.from_numpy(np.stack([synth.pack10(r) for r in xi])).cuda(), 100e6, packed=True).cpu().numpy()
+    variant = ddc.last_variant
+    yf = ddc.run_tensor(torch.from_numpy(xi.astype(np.float32)).cuda(), 100e6).cpu().numpy()
+    assert "generic" not in variant, variant
+    assert np.array_equal(yp, yf) or np.abs(yp - yf).max() <= TOL_MAX * np.abs(yf).max(), variant
+    ref = orc.ddc_reference(xi[1].astype(np.float32), 100e6, tp, d, FS)
+    emax, el2 = rel_err(yp[1], ref)
+    k = 4 if t > 256 else 1
+    assert emax <= k * TOL_MAX and el2 <= k * TOL_L2, (variant, emax, el2)
