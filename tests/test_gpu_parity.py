@@ -501,3 +501,33 @@ def test_packed_input_any_filter(d, t, tmp_path):
     emax, el2 = rel_err(yp[1], ref)
     k = 4 if t > 256 else 1
     assert emax <= k * TOL_MAX and el2 <= k * TOL_L2, (variant, emax, el2)
+
+
+def test_randomised_dispatch_fuzz(tmp_path):
+    """Seeded random (T, D, N, streams, fc): whatever kernel the dispatcher picks (fast FIR, sliced / tensor-staged, sub-filter,
+    phase-major, tile, generic + tails) must agree with the oracle.  Guards the seams between the kernel families."""
+    from scipy import signal
+
+    rng = np.random.default_rng(20261018)
+    seen = set()
+    for case in range(48):
+        d = int(rng.choice([4, 8, 16, 32, 64, 16, 16, 3, 5, 12, 24, 40]))
+        t = int(rng.choice([rng.integers(1, 40), rng.integers(40, 300), rng.integers(300, 1100), 64, 128, 256, 512, 1024]))
+        t = max(t, 2)
+        streams = int(rng.integers(1, 4))
+        n = t + int(rng.integers(0, 90_000))
+        n = n // 4 * 4 if rng.random() < 0.7 else n          # mostly 16-byte aligned rows, sometimes not
+        n = max(n, t)
+        fc = float(rng.choice([100e6, 53.5e6, 428e6, 1.0e6, 855e6]))
+        tp = signal.firwin(t, min(0.8 / d, 0.99)) if t > 3 else np.ones(t)
+        ddc = DigitalDownConverter(d, FS, _custom_taps(tmp_path, tp))
+        xs = np.stack([synth.digitiser_stream(n, 1000 + case * 7 + s) for s in range(streams)]).astype(np.float32)
+        y = ddc.run_tensor(torch.from_numpy(xs).cuda(), fc).cpu().numpy()
+        seen.add(ddc.last_variant.split("<")[0])
+        ref = np.stack([orc.ddc_reference(r, fc, tp, d, FS) for r in xs])
+        assert y.shape == ref.shape, (case, d, t, n, y.shape, ref.shape)
+        emax, el2 = rel_err(y, ref)
+        k = 4 if t > 256 else 1
+        assert emax <= k * TOL_MAX and el2 <= k * TOL_L2, (case, d, t, n, streams, fc, ddc.last_variant, emax, el2)
+    print("kernel families exercised:", sorted(seen))
+    assert len(seen) >= 5, seen
