@@ -459,6 +459,217 @@ ddc_fused_w_kernel(const __grid_constant__ RunParams p,
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Sixteen compute warps: two warps per chunk, each taking half of the phase groups ("kernel W2X").
+//
+// With one warp per chunk only 8 compute warps fit the 13-slot ring, i.e. two per scheduler, and the FMA pipe idles ~11 % of
+// the time (pass boundaries, dependency bubbles) however the loop is arranged: stagger, prefetch and tap-fetch experiments
+// all left the compute-only time at 0.229 ms.  Here warps w and w + 8 share chunk slot and work: w runs phase groups 0, 1 of
+// the chunk, w + 8 phase groups 2, 3, both over all eight outputs of every thread-row.  The partial sums meet through the
+// (by then dead) head of the chunk slot: each warp finishes four of the eight outputs (and their deferred epilogue).
+// Four warps per scheduler at 110 registers is exactly what the register file holds (576 threads x 112).
+// MEASURED: 0.248 ms against 0.244 ms for one warp per chunk -- the two named-barrier rendezvous and the doubled per-chunk
+// bookkeeping eat what the extra warps gain.  Kept behind option "variant" = 12 as a documented experiment.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int D, int JT>
+__global__ void __launch_bounds__(2 * WCfg<D, JT>::NWARPS * 32 + 32 * WCfg<D, JT>::NPROD, 1)
+ddc_fused_w2x_kernel(const __grid_constant__ RunParams p, const __grid_constant__ TapsParam<WCfg<D, JT>::NTW> taps) {
+    using C = WCfg<D, JT>;
+    constexpr int ROW = C::ROW, R = C::R, NW = C::NWP, NWARPS = C::NWARPS, NG = C::NGROUPS;
+    constexpr int NSLOT = C::NSLOT, RH = C::RH, JP = C::JP;
+    constexpr int WANT = C::TOT_ROWS * ROW;
+    constexpr int RO = R / 2;          // outputs a warp finishes
+    static_assert(C::NJG == 1 && C::V == 4 && R == 8, "two-warps-per-chunk variant: D = 16, at most 16 tap blocks");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* empty_bar = full_bar + 16;
+    volatile int* slot_seq = reinterpret_cast<volatile int*>(smem_raw + 384);
+    float* buf = reinterpret_cast<float*>(smem_raw + C::HDR_BYTES);
+
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int lane = tid & 31;
+    if (tid == 0) {
+#pragma unroll 1
+        for (int s = 0; s < NSLOT; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 2);      // both warps of a pair hand the slot back
+            slot_seq[s] = -1;
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int cps = (int)p.tiles_per_stream;
+    const int n_k = (int)((p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    const unsigned long long chunk_dph = (unsigned long long)((long long)C::CHUNK_OUT * D) * p.step_fx;
+
+    if (warp >= 2 * NWARPS) {
+        // ------------------------------------------------------------------ producer warps (as in ddc_fused_w_kernel)
+        constexpr int NP = C::NPROD;
+        const int pid = warp - 2 * NWARPS;
+        const long long pstride = (long long)NP * gridDim.x;
+        const int gs = (int)(pstride / cps), gc = (int)(pstride % cps);
+        const long long pfirst = blockIdx.x + (long long)pid * gridDim.x;
+        int cs = (int)(pfirst / cps), cc = (int)(pfirst % cps);
+        const int sbase = C::sub_base(pid), scnt = C::sub_count(pid);
+        int sidx = 0;
+        uint32_t par = 1;
+        for (int k = pid; k < n_k; k += NP) {
+            const int slot = sbase + sidx;
+            const bool leader = elect_one();
+            if (leader) {
+                mbar_wait(&empty_bar[slot], par);
+                slot_seq[slot] = k;
+            }
+            __syncwarp();
+            const float* src = reinterpret_cast<const float*>(p.in) + (long long)cs * p.in_stride + (long long)cc * C::CHUNK_S;
+            float* dst = buf + (size_t)slot * C::SLOT_FLOATS;
+            const long long valid = p.n_samples - (long long)cc * C::CHUNK_S;
+            if (valid >= WANT) {
+                if (leader) {
+                    mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)WANT * 4u);
+#pragma unroll
+                    for (int sr = 0; sr < C::NSR; ++sr) {
+                        constexpr int SR4 = C::SROWS;
+                        const int nrow = (C::TOT_ROWS - sr * SR4) < SR4 ? (C::TOT_ROWS - sr * SR4) : SR4;
+                        bulk_g2s(dst + sr * C::SRP, src + sr * SR4 * ROW, (uint32_t)nrow * ROW * 4u, &full_bar[slot]);
+                    }
+                }
+            } else {
+                uint32_t tx = 0;
+                for (int sr = 0; sr < C::NSR; ++sr) {
+                    const int cap = ((C::TOT_ROWS - sr * C::SROWS) < C::SROWS ? (C::TOT_ROWS - sr * C::SROWS) : C::SROWS) * ROW;
+                    const long long s0 = (long long)sr * C::SROWS * ROW;
+                    long long cnt = valid - s0;
+                    cnt = cnt < 0 ? 0 : (cnt > cap ? cap : cnt);
+                    const int bulk = (int)cnt & ~3;
+                    for (int e = bulk + lane; e < cap; e += 32) dst[sr * C::SRP + e] = (e < (int)cnt) ? src[s0 + e] : 0.f;
+                    tx += (uint32_t)bulk * 4u;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&full_bar[slot], tx);
+                    for (int sr = 0; sr < C::NSR; ++sr) {
+                        const int cap = ((C::TOT_ROWS - sr * C::SROWS) < C::SROWS ? (C::TOT_ROWS - sr * C::SROWS) : C::SROWS) * ROW;
+                        const long long s0 = (long long)sr * C::SROWS * ROW;
+                        long long cnt = valid - s0;
+                        cnt = cnt < 0 ? 0 : (cnt > cap ? cap : cnt);
+                        const int bulk = (int)cnt & ~3;
+                        if (bulk > 0) bulk_g2s(dst + sr * C::SRP, src + s0, (uint32_t)bulk * 4u, &full_bar[slot]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (++sidx == scnt) { sidx = 0; par ^= 1u; }
+            cs += gs;
+            cc += gc;
+            if (cc >= cps) { cc -= cps; ++cs; }
+        }
+    } else {
+        // ------------------------------------------------------------------ compute warps: pair grp = warp % 8, half hw = warp / 8
+        const int grp = warp % NG;
+        const int hw = warp / NG;
+        const int g = (lane & 7) * C::SROWS + (lane >> 3);
+        int rowoff[C::HALO_ROWS + 1];
+#pragma unroll
+        for (int h = 0; h <= C::HALO_ROWS; ++h) rowoff[h] = C::row_offset(g + h);
+        float2 rot_thr[RO];   // my outputs of the thread-row: r = RO hw .. RO hw + RO - 1
+#pragma unroll
+        for (int r = 0; r < RO; ++r) rot_thr[r] = nco_rot((unsigned long long)((long long)(g * R + RO * hw + r) * D) * p.step_fx);
+
+        const long long kstride = (long long)NG * gridDim.x;
+        const int gs = (int)(kstride / cps), gc = (int)(kstride % cps);
+        const long long first = blockIdx.x + (long long)grp * gridDim.x;
+        int cs = (int)(first / cps), cc = (int)(first % cps);
+        const int sbase = C::sub_base(grp % C::NPROD), scnt = C::sub_count(grp % C::NPROD);
+        int sidx = (grp / C::NPROD) % scnt;
+        uint32_t par = (uint32_t)((grp / C::NPROD) / scnt) & 1u;
+        const int bar_id = 1 + grp;   // named barrier of the pair (64 threads)
+
+        float2 yprev[RO];
+#pragma unroll
+        for (int r = 0; r < RO; ++r) yprev[r] = make_float2(0.f, 0.f);
+        long long prev_m0 = 0;
+        float2* prev_o = p.out;
+        int prev_cc = 0;
+        long long prev_nout = 0;
+        float2 m0a[RH], m1a[RH], m2a[RH];
+
+        for (int k = grp; k < n_k; k += NG) {
+            const int slot = sbase + sidx;
+            while (slot_seq[slot] != k) {}
+            mbar_wait(&full_bar[slot], par);
+            float* sbuf = buf + (size_t)slot * C::SLOT_FLOATS;
+#pragma unroll
+            for (int r = 0; r < RH; ++r) m0a[r] = m1a[r] = m2a[r] = make_float2(0.f, 0.f);
+            // my two phase groups: 2 hw and 2 hw + 1
+            const float4* tp = &taps.c2[4 * hw];
+            int xoff = 8 * hw;
+            asm volatile("" : "+r"(xoff));
+            {
+                float4 w[NW];
+#pragma unroll
+                for (int b = 0; b < NW; ++b)
+                    w[b] = *reinterpret_cast<const float4*>(sbuf + xoff + rowoff[b / R] + (b % R) * D);
+                w_epilogue<RO>(yprev, rot_thr, p.phase0_fx + (unsigned long long)prev_cc * chunk_dph, prev_m0, prev_o, prev_nout);
+                w_fir_pg<D, JP, R>(w, tp, m0a, m1a, m2a);
+            }
+            {
+                float4 w[NW];
+#pragma unroll
+                for (int b = 0; b < NW; ++b)
+                    w[b] = *reinterpret_cast<const float4*>(sbuf + xoff + 4 + rowoff[b / R] + (b % R) * D);
+                w_fir_pg<D, JP, R>(w, tp + 2, m0a, m1a, m2a);
+            }
+            // both warps are done reading the chunk: its head becomes the exchange area (48 bytes per lane and direction)
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            float4* xs = reinterpret_cast<float4*>(sbuf) + (hw * 32 + lane) * 3;              // what I send
+            const float4* xr = reinterpret_cast<const float4*>(sbuf) + ((hw ^ 1) * 32 + lane) * 3;   // what my partner sent
+            // the pairs my partner finishes: 2, 3 if I am half 0, else 0, 1 (selects, not dynamic indexing: the sums stay in registers)
+            const bool h1 = hw != 0;
+            auto sel = [&](const float2& lo, const float2& hi) { return h1 ? lo : hi; };
+            {
+                const float2 s0 = sel(m0a[0], m0a[2]), s1 = sel(m0a[1], m0a[3]);
+                const float2 t0 = sel(m1a[0], m1a[2]), t1 = sel(m1a[1], m1a[3]);
+                const float2 u0 = sel(m2a[0], m2a[2]), u1 = sel(m2a[1], m2a[3]);
+                xs[0] = make_float4(s0.x, s0.y, s1.x, s1.y);
+                xs[1] = make_float4(t0.x, t0.y, t1.x, t1.y);
+                xs[2] = make_float4(u0.x, u0.y, u1.x, u1.y);
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            const float4 r0 = xr[0], r1 = xr[1], r2 = xr[2];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[slot]);   // the second arrival returns the slot to the producer
+
+            // my output pairs: 2 hw, 2 hw + 1 -> outputs RO hw .. RO hw + 3
+            auto mine = [&](const float2& lo, const float2& hi) { return h1 ? hi : lo; };
+            const float2 k0 = mine(m0a[0], m0a[2]), k1 = mine(m0a[1], m0a[3]);
+            const float2 l0 = mine(m1a[0], m1a[2]), l1 = mine(m1a[1], m1a[3]);
+            const float2 n0 = mine(m2a[0], m2a[2]), n1 = mine(m2a[1], m2a[3]);
+            const float2 a0 = make_float2(k0.x + r0.x, k0.y + r0.y), a1 = make_float2(k1.x + r0.z, k1.y + r0.w);
+            const float2 b0 = make_float2(l0.x + r1.x, l0.y + r1.y), b1 = make_float2(l1.x + r1.z, l1.y + r1.w);
+            const float2 c0 = make_float2(n0.x + r2.x, n0.y + r2.y), c1 = make_float2(n1.x + r2.z, n1.y + r2.w);
+            yprev[0] = make_float2(a0.x + b0.x, a0.y + b0.y);
+            yprev[1] = make_float2(b0.x - c0.x, b0.y - c0.y);
+            yprev[2] = make_float2(a1.x + b1.x, a1.y + b1.y);
+            yprev[3] = make_float2(b1.x - c1.x, b1.y - c1.y);
+            prev_cc = cc;
+            prev_m0 = (long long)cc * C::CHUNK_OUT + g * R + RO * hw;
+            prev_o = p.out + (long long)cs * p.out_stride + prev_m0;
+            prev_nout = p.n_out;
+
+            sidx += NG / C::NPROD;
+            if (sidx >= scnt) { sidx -= scnt; par ^= 1u; }
+            cs += gs;
+            cc += gc;
+            if (cc >= cps) { cc -= cps; ++cs; }
+        }
+        w_epilogue<RO>(yprev, rot_thr, p.phase0_fx + (unsigned long long)prev_cc * chunk_dph, prev_m0, prev_o, prev_nout);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Small decimations (D = 4, 8) on the same machinery: output m = NQ m' + q (NQ = 16 / D) is
 //      y[NQ m' + q] = sum_k c[k] x[16 m' + D q + k] = sum_k' c_q[k'] x[16 m' + k'],      c_q[k'] = c[k' - D q],
 // i.e. NQ interleaved decimate-by-16 filters with SHIFTED tap sets over the SAME staged chunk (T' = T + D (NQ - 1) taps

@@ -421,6 +421,28 @@ int launch_w(ddcb200* h, RunParams& p, cudaStream_t st, double step) {
     return DDCB200_OK;
 }
 
+template <int D, int JT>
+int launch_w2x(ddcb200* h, RunParams& p, cudaStream_t st, double step) {
+    using C = WCfg<D, JT>;
+    auto kern = ddc_fused_w2x_kernel<D, JT>;
+    const size_t smem = C::HDR_BYTES + (size_t)C::NSLOT * C::SLOT_FLOATS * sizeof(float);
+    static bool attr_set[64] = {};
+    if (h->device < 64 && !attr_set[h->device]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[h->device] = true;
+    }
+    TapsParam<C::NTW> tp;
+    std::memcpy(tp.c2, cached_wtaps(h, step, JT, D), sizeof(float2) * (size_t)C::NTW);
+    const long long grid = std::min<long long>(p.total_tiles, h->sm_count);
+    kern<<<(unsigned)grid, 2 * C::NWARPS * 32 + 32 * C::NPROD, smem, st>>>(p, tp);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    char name[96];
+    snprintf(name, sizeof(name), "fused_fast_fir_16w<D%d,R%d,J%d,SLOTS%d>", D, C::R, JT, C::NSLOT);
+    h->last_variant = name;
+    return DDCB200_OK;
+}
+
 template <int D>
 int launch_w_j(ddcb200* h, RunParams& p, cudaStream_t st, double step, int jt, bool nest) {
     if constexpr (D == 16) {   // two nested levels need R = 8 outputs per thread
@@ -800,7 +822,7 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
     const bool long_w = D == 16 && (T + D - 1) / D > 16 && (T + D - 1) / D <= 64 &&
                         (h->force_variant == 0 || h->force_variant == 7 || h->force_variant == 9);
     if (!sliced_done && aligned_f32(d_in, in_stride, packed) && (D == 16 || D == 32 || D == 64) && ((T + D - 1) / D <= 16 || long_w) &&
-        (h->force_variant == 0 || (h->force_variant >= 5 && h->force_variant <= 9))) {
+        (h->force_variant == 0 || (h->force_variant >= 5 && h->force_variant <= 9) || h->force_variant == 12)) {
         const int ksp = (h->force_variant == 6) ? 2 : 1;   // option "variant": 5 (= auto) one warp per chunk, 6 = two (slower)
         const int Jp = (T + D - 1) / D;
         const int jt = Jp <= 4 ? 4 : (Jp <= 8 ? 8 : (Jp <= 16 ? 16 : (Jp <= 32 ? 32 : 64)));
@@ -812,6 +834,7 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         p.m_begin = 0;
         // option "variant": 0 auto; 5 / 6 kernel P with one / two warps per chunk; 7 fast FIR (kernel W); 8 deferred-epilogue P.
         // Auto picks the fast-FIR kernel where a thread has R = 8 outputs (D = 16) and the output rows allow 16-byte stores.
+        if (h->force_variant == 12 && D == 16 && jt == 16) return launch_w2x<16, 16>(h, p, st, step);   // 16 compute warps (experiment)
         const bool want_w = h->force_variant == 7 || h->force_variant == 9 || (h->force_variant == 0 && D == 16);
         if (want_w) {   // any complex64-aligned output: the epilogue picks its 16-byte pairing per thread
             const bool nest = h->force_variant == 9;   // option "variant" 9: two nested fast-FIR levels (D = 16)
