@@ -531,3 +531,21 @@ def test_randomised_dispatch_fuzz(tmp_path):
         assert emax <= k * TOL_MAX and el2 <= k * TOL_L2, (case, d, t, n, streams, fc, ddc.last_variant, emax, el2)
     print("kernel families exercised:", sorted(seen))
     assert len(seen) >= 5, seen
+
+
+@pytest.mark.parametrize("variant,name", [(7, "fused_fast_fir<"), (8, "deferred"), (9, "nested"), (12, "16w"), (5, "phase_major<")])
+def test_optional_kernel_variants_stay_correct(taps_dir, variant, name):
+    """The documented experiments and fall-backs behind option `variant` keep producing reference results."""
+    n = (1 << 21) + 4 * 333
+    xs = np.stack([synth.digitiser_stream_fast(n, 60 + s) for s in range(2)]).astype(np.float32)
+    ddc = _ddc(taps_dir, 16)
+    ddc.set_option("variant", variant)
+    y = ddc.run_tensor(torch.from_numpy(xs).cuda(), 100e6).cpu().numpy()
+    assert name in ddc.last_variant, ddc.last_variant
+    step = orc.phase_step_cycles(n, 100e6, FS)
+    m = y.shape[1]
+    scale = np.abs(y).max()
+    for s in range(2):
+        for s0 in (0, 70_000, m - 512):
+            ref = orc.ddc_windowed_f64(xs[s], s0, 512, step, ddc.ddc_filter_coeffs, 16)
+            assert np.abs(y[s, s0:s0 + 512] - ref).max() <= TOL_MAX * scale, (variant, s, s0)
