@@ -409,6 +409,8 @@ def run_ours(args):
         del full
 
     # ---- max over ranks -------------------------------------------------------------------------------------------
+    if os.environ.get("DDCB200_BENCH_VERBOSE"):
+        print(f"[rank {rank}] device {total_ms / args.steps:.4f} ms/step, e2e {e2e_s * 1e3:.2f} ms/step", file=sys.stderr, flush=True)
     stats = torch.tensor([total_ms, e2e_s, float(np.median(kern_ms))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
