@@ -174,7 +174,15 @@ int ddcb200_version(void);
 int64_t ddcb200_launch_count(ddcb200_t* handle);
 /* Name of the kernel variant the last run on this handle dispatched to (e.g. "fused_tma<D16,R4,T256>"). */
 const char* ddcb200_last_variant(ddcb200_t* handle);
-/* Tuning/diagnostic knobs: "variant" (0 = auto, 1 = force generic kernel), "chunk_samples" (host path). */
+/* Tuning/diagnostic knobs (all optional; 0 restores the default):
+ *   "variant"        kernel choice: 0 auto, 1 generic, 2/3 tile kernel, 5/6 phase-major direct form, 7 fast FIR, 8 deferred-
+ *                    epilogue direct form, 9 nested fast FIR, 10 warp-specialised packed kernel, 11 tensor-staged / sliced
+ *                    fast FIR, 12 sixteen-compute-warp fast FIR (see DESIGN.md section 4 and tools/README.md);
+ *   "chunk_samples"  time-chunk size of the host path (default 2^24 samples per launch);
+ *   "copy_threads"   host threads that stage pageable input through pinned buffers and widen complex128 output (default 4,
+ *                    0 = leave pageable copies to the driver);
+ *   "debug_mode", "dbg_counters", "l2_ahead", "stagger_cycles"   measurement aids of the kernels (compute-only / memory-only
+ *                    ceilings, ring wait-time counters). */
 int ddcb200_set_option(ddcb200_t* handle, const char* key, int64_t value);
 
 #ifdef __cplusplus
