@@ -43,16 +43,25 @@ struct WSCfg {
     // (The 128-byte swizzle pads every 64-byte box row to a 128-byte line: tools/microbench/tma_swizzle_probe.cu.)
     // With 32-byte lines (D = 8) the 32-byte swizzle does the same job (unit ^= (row / 4) % 2, bits 5-6 = row % 4); 16-byte
     // lines (D = 4) are conflict-free as they are.
+    // D = 4 / 8 with short filters (JT * D <= 64 taps, the HBM-bound cells): WHOLE-row tiles instead.  A thread-row is only
+    // 128 / 256 bytes, so a line of a tile is a whole thread-row (D = 4) or half of one (D = 8) -- 128 contiguous bytes of the
+    // input -- written with the 128-byte swizzle (unit ^= row % 8).  One / two copies per chunk instead of eight: the per-block
+    // tiles with 16 / 32-byte lines are TMA-bound there (4.2-4.9 TB/s), the whole-row tiles reach 4.4 TB/s (D = 4, T = 64) and
+    // 6.2 TB/s (D = 8, T = 64).  Longer filters are FP32-bound and keep the per-block tiles, whose window addressing is
+    // cheaper (T = 128: 0.132 / 0.071 ms against 0.142 / 0.072 ms at D = 4 / 8).
+    static constexpr bool WHOLE = D < 16 && JT * D <= 64;
     static constexpr int SLOT_ROWS = 36;           // 32 + up to 4 halo rows
-    static constexpr int LINE_BYTES = DB * 4;      // 64 / 32 / 16
-    static constexpr int TILE_BYTES = 40 * LINE_BYTES;         // per block index: 36 lines, pitch a multiple of the swizzle period
-    static constexpr int SLOT_BYTES = R * TILE_BYTES;          // 20 / 10 / 5 KB
-    static constexpr int TX_BYTES = R * SLOT_ROWS * LINE_BYTES;   // bytes landed per slot
+    static constexpr int LINE_BYTES = WHOLE ? 128 : DB * 4;          // 128 / 64 / 32 / 16
+    static constexpr int NTILE = WHOLE ? (ROW * 4) / 128 : R;        // copies per slot: 1 (D = 4), 2 (D = 8); 8 per-block tiles
+    static constexpr int TILE_BYTES = 40 * LINE_BYTES;               // 36 lines, pitch a multiple of the swizzle period
+    static constexpr int SLOT_BYTES = NTILE * TILE_BYTES;
+    static constexpr int TX_BYTES = NTILE * SLOT_ROWS * LINE_BYTES;  // bytes landed per slot
     static constexpr int HDR_BYTES = 1024;
     static constexpr int NGROUPS = 8, NWARPS = 8, NPROD = 2;
     static constexpr int NSLOT_MAX = (227 * 1024 - HDR_BYTES - 1024) / SLOT_BYTES;
     static constexpr int NSLOT = NSLOT_MAX > 16 ? 16 : NSLOT_MAX;   // 11 at D >= 32
     static_assert(NSLOT >= NGROUPS + 2 && NSLOT <= 16, "ring size");
+    // per-block tiles: 64-byte swizzle (16-float lines), 32-byte swizzle (8-float lines), none (4-float lines)
     __host__ __device__ static constexpr int swz(int row) { return DB == 16 ? ((row >> 1) & 3) : (DB == 8 ? ((row >> 2) & 1) : 0); }
     static constexpr int CHUNK_ROWS = 32;
     static constexpr int CHUNK_OUT = CHUNK_ROWS * R;       // 256 outputs
@@ -83,7 +92,7 @@ ddc_fused_ws_kernel(const __grid_constant__ RunParams p, const __grid_constant__
                     const __grid_constant__ TapsParam<WSCfg<D, JT>::NTW> taps) {
     using C = WSCfg<D, JT>;
     constexpr int R = C::R, NW = C::NWP, NWARPS = C::NWARPS, NG = C::NGROUPS, NSLOT = C::NSLOT, RH = C::RH;
-    constexpr int LPQ = C::LPQ, JP = C::JP, NJG = C::NJG, ROW = C::ROW;
+    constexpr int LPQ = C::LPQ, JP = C::JP, NJG = C::NJG;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -135,7 +144,7 @@ ddc_fused_ws_kernel(const __grid_constant__ RunParams p, const __grid_constant__
                 // NOT fully unrolled: eight UTMALDG in a row need so many uniform registers that ptxas stops using the uniform
                 // datapath for the whole kernel -- the consumers' tap fetches turn from LDCU into per-thread LDC (2.2x slower)
 #pragma unroll 4
-                for (int b = 0; b < R; ++b) tma_load_5d(dst + b * C::TILE_BYTES, &tmap, 0, q, b, row0, cs, &full_bar[slot]);
+                for (int b = 0; b < C::NTILE; ++b) tma_load_5d(dst + b * C::TILE_BYTES, &tmap, 0, q, b, row0, cs, &full_bar[slot]);
             }
             __syncwarp();
             if (++sidx == scnt) { sidx = 0; par ^= 1u; }
@@ -148,13 +157,29 @@ ddc_fused_ws_kernel(const __grid_constant__ RunParams p, const __grid_constant__
         // tile blk at line `row`, logical 16-byte unit pgv, physical unit pgv ^ swz(row).
         auto load_window = [&](float4(&w)[NW], const unsigned char* sb, int grow, int pgv) {
             int a[C::WROWS];
+            if constexpr (C::WHOLE) {
+                // byte offset of (blk, pgv) inside its thread-row: blk * 4 D + 16 pgv -> tile = offset / 128, unit = rest / 16,
+                // physical unit = unit ^ (row % 8).  blk * 4 D is static; 16 pgv only touches bit 4 (D = 8) or is zero (D = 4).
 #pragma unroll
-            for (int h = 0; h < C::WROWS; ++h) {
-                const int row = grow + h;
-                a[h] = row * C::LINE_BYTES + ((pgv ^ C::swz(row)) << 4);
+                for (int h = 0; h < C::WROWS; ++h) {
+                    const int row = grow + h;
+                    a[h] = ((row & 7) << 4) ^ (pgv << 4);   // XOR mask of this row (and phase group)
+                }
+#pragma unroll
+                for (int b = 0; b < NW; ++b) {
+                    const int h = b / R, blk = b % R;
+                    const int off = blk * 4 * D;            // static
+                    w[b] = *reinterpret_cast<const float4*>(sb + (off >> 7) * C::TILE_BYTES + (grow + h) * 128 + ((off & 127) ^ a[h]));
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < C::WROWS; ++h) {
+                    const int row = grow + h;
+                    a[h] = row * C::LINE_BYTES + ((pgv ^ C::swz(row)) << 4);
+                }
+#pragma unroll
+                for (int b = 0; b < NW; ++b) w[b] = *reinterpret_cast<const float4*>(sb + a[b / R] + (b % R) * C::TILE_BYTES);
             }
-#pragma unroll
-            for (int b = 0; b < NW; ++b) w[b] = *reinterpret_cast<const float4*>(sb + a[b / R] + (b % R) * C::TILE_BYTES);
         };
         float2 rot_thr[R];
 #pragma unroll

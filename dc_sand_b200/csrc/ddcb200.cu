@@ -576,18 +576,24 @@ PFN_encodeTiled get_encode_tiled() {
     return fn;
 }
 
-// dims (fastest first): DB floats of a slice (DB = min(D, 16)), D/16 slices (1 for D < 16), 8 blocks of a thread-row,
-// thread-rows, streams; box = (DB, 1, 1, 36, 1): the slice of one block index for the 36 thread-rows of a slot, lines of
-// DB * 4 bytes written with the swizzle of that span (64 B / 32 B / none)
-int make_slice_tmap(const float* d_in, int D, long long n_rows, long long n_streams, long long in_stride, CUtensorMap* out) {
+// Per-block tiles: dims (fastest first) DB floats of a slice (DB = min(D, 16)), D/16 slices (1 for D < 16), 8 blocks of a
+// thread-row, thread-rows, streams; box = (DB, 1, 1, 36, 1): the slice of one block index for the 36 thread-rows of a slot,
+// lines of DB * 4 bytes written with the swizzle of that span (64 B / 32 B / none).
+// Whole-row tiles (D = 4 / 8, short filters -- WSCfg::WHOLE): dims (32 floats = 128 bytes, 1, 128-byte pieces of a thread-row,
+// thread-rows, streams), box (32, 1, 1, 36, 1), 128-byte swizzle; the same coordinate order (0, slice, tile, row, stream).
+int make_slice_tmap(const float* d_in, int D, bool whole, long long n_rows, long long n_streams, long long in_stride, CUtensorMap* out) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return fail(DDCB200_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
     const int DB = D < 16 ? D : 16;
-    const cuuint64_t gdim[5] = {(cuuint64_t)DB, (cuuint64_t)(D < 16 ? 1 : D / 16), 8, (cuuint64_t)n_rows, (cuuint64_t)n_streams};
-    const cuuint64_t gstr[4] = {64, (cuuint64_t)D * 4, (cuuint64_t)D * 32, (cuuint64_t)in_stride * 4};
-    const cuuint32_t box[5] = {(cuuint32_t)DB, 1, 1, 36, 1};
+    const cuuint64_t gdim[5] = {(cuuint64_t)(whole ? 32 : DB), (cuuint64_t)(D < 16 ? 1 : D / 16), (cuuint64_t)(whole ? D / 4 : 8),
+                                (cuuint64_t)n_rows, (cuuint64_t)n_streams};
+    const cuuint64_t gstr[4] = {(cuuint64_t)(whole ? 128 : 64), (cuuint64_t)(whole ? 128 : D * 4), (cuuint64_t)D * 32,
+                                (cuuint64_t)in_stride * 4};
+    const cuuint32_t box[5] = {(cuuint32_t)(whole ? 32 : DB), 1, 1, 36, 1};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    const CUtensorMapSwizzle sw = DB == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : (DB == 8 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE);
+    const CUtensorMapSwizzle sw = whole      ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : DB == 16 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                             : (DB == 8 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE);
     const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(d_in), gdim, gstr, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(DDCB200_ECUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
@@ -604,7 +610,7 @@ int launch_ws(ddcb200* h, RunParams& p, const float* d_in, long long n_rows, cud
         attr_set[h->device] = true;
     }
     CUtensorMap tmap;
-    int rc = make_slice_tmap(d_in, D, n_rows, p.n_streams, p.in_stride, &tmap);
+    int rc = make_slice_tmap(d_in, D, C::WHOLE, n_rows, p.n_streams, p.in_stride, &tmap);
     if (rc) return rc;
     TapsParam<C::NTW> tp;
     std::memcpy(tp.c2, cached_wtaps(h, step, JT, D), sizeof(float2) * (size_t)C::NTW);
@@ -613,7 +619,7 @@ int launch_ws(ddcb200* h, RunParams& p, const float* d_in, long long n_rows, cud
     CUDA_TRY(cudaGetLastError());
     h->launches++;
     char name[96];
-    snprintf(name, sizeof(name), "fused_fast_fir_%s<D%d,R%d,J%d,SLICES%d,SLOTS%d>", D >= 32 ? "sliced" : "tensor_staged", D, C::R, JT, C::LPQ,
+    snprintf(name, sizeof(name), "fused_fast_fir_%s<D%d,R%d,J%d,SLICES%d,SLOTS%d>", D >= 32 ? "sliced" : (C::WHOLE ? "row_staged" : "tensor_staged"), D, C::R, JT, C::LPQ,
              C::NSLOT);
     h->last_variant = name;
     return DDCB200_OK;
@@ -770,9 +776,9 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         const bool fp32_bound = 4.0 * T / D > 11.4 * (4.0 + 8.0 / D);
         // D = 4 / 8: the same tensor-staged kernel with whole blocks (R = 8 outputs per thread); auto for short filters only,
         // where the rotating-window tile kernel is weakest (see profiles/r1_sweep_taps_decimation.md)
-        // measured at N = 2^26 against the tile kernel: D = 4: T = 64 0.095 vs 0.128 ms, T = 128 0.132 vs 0.173; D = 8: T = 128 0.070 vs
-        // 0.083, but T = 64 0.069 vs 0.062 (HBM-bound) and T = 256 0.160 vs 0.141
-        const bool small_auto = (D == 4 && T <= 128) || (D == 8 && T > 64 && T <= 128);
+        // measured at N = 2^26 against the tile kernel: D = 4: T = 64 0.090 vs 0.128 ms, T = 128 0.132 vs 0.173; D = 8: T = 64 0.054
+        // vs 0.062, T = 128 0.070 vs 0.083, but T = 256 0.160 vs 0.141 (T * D <= 64 padded taps: whole-row tiles, WSCfg::WHOLE)
+        const bool small_auto = (D == 4 || D == 8) && T <= 128;
         const bool small_d = (D == 4 || D == 8) && (h->force_variant == 11 || (h->force_variant == 0 && small_auto));
         if (aligned_f32(d_in, in_stride, packed) && Jp <= 32 && T >= D &&
             (small_d || ((D == 32 || D == 64) && (h->force_variant == 11 || (h->force_variant == 0 && fp32_bound))))) {
