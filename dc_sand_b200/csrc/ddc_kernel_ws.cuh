@@ -19,7 +19,7 @@ namespace ddck {
 
 template <int D, int JT>
 struct WSCfg {
-    static_assert(D == 4 || D == 8 || D == 32 || D == 64, "tensor-staged kernel: D = 32, 64 (sliced) and D = 4, 8 (whole blocks)");
+    static_assert(D == 4 || D == 8 || D == 16 || D == 32 || D == 64, "tensor-staged kernel: D = 32, 64 (sliced) and D = 4, 8, 16 (whole blocks)");
     static_assert(JT % 2 == 0 && JT <= 32, "tap blocks: even, at most 32 (halo of four thread-rows)");
     // D = 4 / 8 use the same staging with ONE slice that holds the whole D-sample block: thread-rows of 8 blocks (32 / 64
     // samples) give R = 8 outputs per thread, which the 1-D kernels (128-sample rows) cannot offer at these decimations.
@@ -49,7 +49,7 @@ struct WSCfg {
     // tiles with 16 / 32-byte lines are TMA-bound there (4.2-4.9 TB/s), the whole-row tiles reach 4.4 TB/s (D = 4, T = 64) and
     // 6.2 TB/s (D = 8, T = 64).  Longer filters are FP32-bound and keep the per-block tiles, whose window addressing is
     // cheaper (T = 128: 0.132 / 0.071 ms against 0.142 / 0.072 ms at D = 4 / 8).
-    static constexpr bool WHOLE = D < 16 && JT * D <= 64;
+    static constexpr bool WHOLE = (D < 16 && JT * D <= 64) || (D == 16 && JT <= 8);
     static constexpr int SLOT_ROWS = 36;           // 32 + up to 4 halo rows
     static constexpr int LINE_BYTES = WHOLE ? 128 : DB * 4;          // 128 / 64 / 32 / 16
     static constexpr int NTILE = WHOLE ? (ROW * 4) / 128 : R;        // copies per slot: 1 (D = 4), 2 (D = 8); 8 per-block tiles

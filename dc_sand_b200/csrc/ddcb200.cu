@@ -778,8 +778,10 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         // where the rotating-window tile kernel is weakest (see profiles/r1_sweep_taps_decimation.md)
         // measured at N = 2^26 against the tile kernel: D = 4: T = 64 0.090 vs 0.128 ms, T = 128 0.132 vs 0.173; D = 8: T = 64 0.054
         // vs 0.062, T = 128 0.070 vs 0.083, but T = 256 0.160 vs 0.141 (T * D <= 64 padded taps: whole-row tiles, WSCfg::WHOLE)
-        const bool small_auto = (D == 4 || D == 8) && T <= 128;
-        const bool small_d = (D == 4 || D == 8) && (h->force_variant == 11 || (h->force_variant == 0 && small_auto));
+        // D = 16: whole-row tiles for the HBM-bound filters (T <= 128: 0.0517 against 0.0524 / 0.0537 ms of the 1-D bulk-copy kernel);
+        // longer filters are much slower here than in ddc_kernel_w.cuh (T = 256: 0.312 vs 0.244 ms at 2^28) -- option 11 only
+        const bool small_auto = ((D == 4 || D == 8 || D == 16) && T <= 128);
+        const bool small_d = (D == 4 || D == 8 || D == 16) && (h->force_variant == 11 || (h->force_variant == 0 && small_auto));
         if (aligned_f32(d_in, in_stride, packed) && Jp <= 32 && T >= D &&
             (small_d || ((D == 32 || D == 64) && (h->force_variant == 11 || (h->force_variant == 0 && fp32_bound))))) {
             const int jt = Jp <= 8 ? 8 : (Jp <= 16 ? 16 : 32);
@@ -797,6 +799,7 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
                 const float* fin = reinterpret_cast<const float*>(d_in);
                 int rc2 = D == 4    ? launch_ws_j<4>(h, p, fin, n_blocks / 8, st, step, jt)
                           : D == 8  ? launch_ws_j<8>(h, p, fin, n_blocks / 8, st, step, jt)
+                          : D == 16 ? launch_ws_j<16>(h, p, fin, n_blocks / 8, st, step, jt)
                           : D == 32 ? launch_ws_j<32>(h, p, fin, n_blocks / 8, st, step, jt)
                                     : launch_ws_j<64>(h, p, fin, n_blocks / 8, st, step, jt);
                 if (rc2) return rc2;
