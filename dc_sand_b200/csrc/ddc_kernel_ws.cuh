@@ -20,7 +20,7 @@ namespace ddck {
 template <int D, int JT>
 struct WSCfg {
     static_assert(D == 4 || D == 8 || D == 16 || D == 32 || D == 64, "tensor-staged kernel: D = 32, 64 (sliced) and D = 4, 8, 16 (whole blocks)");
-    static_assert(JT % 2 == 0 && JT <= 32, "tap blocks: even, at most 32 (halo of four thread-rows)");
+    static_assert(JT % 2 == 0 && (JT <= 32 || (JT == 64 && D < 16)), "tap blocks: even, at most 32 (halo of four thread-rows); 64 at D = 4 / 8 (eight)");
     // D = 4 / 8 use the same staging with ONE slice that holds the whole D-sample block: thread-rows of 8 blocks (32 / 64
     // samples) give R = 8 outputs per thread, which the 1-D kernels (128-sample rows) cannot offer at these decimations.
     static constexpr int LPQ = D < 16 ? 1 : D / 16;   // slices per chunk
@@ -50,7 +50,7 @@ struct WSCfg {
     // 6.2 TB/s (D = 8, T = 64).  Longer filters are FP32-bound and keep the per-block tiles, whose window addressing is
     // cheaper (T = 128: 0.132 / 0.071 ms against 0.142 / 0.072 ms at D = 4 / 8).
     static constexpr bool WHOLE = (D < 16 && JT * D <= 64) || (D == 16 && JT <= 8);
-    static constexpr int SLOT_ROWS = 36;           // 32 + up to 4 halo rows
+    static constexpr int SLOT_ROWS = JT > 32 ? 40 : 36;              // 32 + up to 4 (8) halo rows
     static constexpr int LINE_BYTES = WHOLE ? 128 : DB * 4;          // 128 / 64 / 32 / 16
     static constexpr int NTILE = WHOLE ? (ROW * 4) / 128 : R;        // copies per slot: 1 (D = 4), 2 (D = 8); 8 per-block tiles
     static constexpr int TILE_BYTES = 40 * LINE_BYTES;               // 36 lines, pitch a multiple of the swizzle period
@@ -59,7 +59,11 @@ struct WSCfg {
     static constexpr int HDR_BYTES = 1024;
     static constexpr int NGROUPS = 8, NWARPS = 8, NPROD = 2;
     static constexpr int NSLOT_MAX = (227 * 1024 - HDR_BYTES - 1024) / SLOT_BYTES;
-    static constexpr int NSLOT = NSLOT_MAX > 16 ? 16 : NSLOT_MAX;   // 11 at D >= 32
+    // D = 4 / 8 with whole-row tiles: TWO CTAs per SM (the slots are small, and 20 warps hide the ring and pipe latencies that
+    // 10 cannot: ncu shows the FMA pipe 65 % active and DRAM at 48 % with one CTA); the ring is cut to what two CTAs can hold
+    static constexpr int CTAS = (D == 4 || (D == 8 && !WHOLE)) ? 2 : 1;
+    static constexpr int NSLOT_FIT = NSLOT_MAX / CTAS > 16 ? 16 : NSLOT_MAX / CTAS;
+    static constexpr int NSLOT = (CTAS == 2 && NSLOT_FIT > 12) ? 12 : NSLOT_FIT;   // 11 at D >= 32
     static_assert(NSLOT >= NGROUPS + 2 && NSLOT <= 16, "ring size");
     // per-block tiles: 64-byte swizzle (16-float lines), 32-byte swizzle (8-float lines), none (4-float lines)
     __host__ __device__ static constexpr int swz(int row) { return DB == 16 ? ((row >> 1) & 3) : (DB == 8 ? ((row >> 2) & 1) : 0); }
@@ -87,7 +91,7 @@ __device__ __forceinline__ void tma_load_5d(void* dst_smem, const CUtensorMap* t
 // handles in its round-th turn (local chunk index round * 8 + w).  Producer p stages positions = p (mod 2) in order, into
 // its own sub-ring; warp w consumes positions w, w + 8, ...: consumption order matches staging order.
 template <int D, int JT>
-__global__ void __launch_bounds__(WSCfg<D, JT>::NWARPS * 32 + 32 * WSCfg<D, JT>::NPROD, 1)
+__global__ void __launch_bounds__(WSCfg<D, JT>::NWARPS * 32 + 32 * WSCfg<D, JT>::NPROD, WSCfg<D, JT>::CTAS)
 ddc_fused_ws_kernel(const __grid_constant__ RunParams p, const __grid_constant__ CUtensorMap tmap,
                     const __grid_constant__ TapsParam<WSCfg<D, JT>::NTW> taps) {
     using C = WSCfg<D, JT>;

@@ -581,7 +581,7 @@ PFN_encodeTiled get_encode_tiled() {
 // lines of DB * 4 bytes written with the swizzle of that span (64 B / 32 B / none).
 // Whole-row tiles (D = 4 / 8, short filters -- WSCfg::WHOLE): dims (32 floats = 128 bytes, 1, 128-byte pieces of a thread-row,
 // thread-rows, streams), box (32, 1, 1, 36, 1), 128-byte swizzle; the same coordinate order (0, slice, tile, row, stream).
-int make_slice_tmap(const float* d_in, int D, bool whole, long long n_rows, long long n_streams, long long in_stride, CUtensorMap* out) {
+int make_slice_tmap(const float* d_in, int D, bool whole, int slot_rows, long long n_rows, long long n_streams, long long in_stride, CUtensorMap* out) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return fail(DDCB200_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
     const int DB = D < 16 ? D : 16;
@@ -589,7 +589,7 @@ int make_slice_tmap(const float* d_in, int D, bool whole, long long n_rows, long
                                 (cuuint64_t)n_rows, (cuuint64_t)n_streams};
     const cuuint64_t gstr[4] = {(cuuint64_t)(whole ? 128 : 64), (cuuint64_t)(whole ? 128 : D * 4), (cuuint64_t)D * 32,
                                 (cuuint64_t)in_stride * 4};
-    const cuuint32_t box[5] = {(cuuint32_t)(whole ? 32 : DB), 1, 1, 36, 1};
+    const cuuint32_t box[5] = {(cuuint32_t)(whole ? 32 : DB), 1, 1, (cuuint32_t)slot_rows, 1};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     const CUtensorMapSwizzle sw = whole      ? CU_TENSOR_MAP_SWIZZLE_128B
                                   : DB == 16 ? CU_TENSOR_MAP_SWIZZLE_64B
@@ -610,11 +610,11 @@ int launch_ws(ddcb200* h, RunParams& p, const float* d_in, long long n_rows, cud
         attr_set[h->device] = true;
     }
     CUtensorMap tmap;
-    int rc = make_slice_tmap(d_in, D, C::WHOLE, n_rows, p.n_streams, p.in_stride, &tmap);
+    int rc = make_slice_tmap(d_in, D, C::WHOLE, C::SLOT_ROWS, n_rows, p.n_streams, p.in_stride, &tmap);
     if (rc) return rc;
     TapsParam<C::NTW> tp;
     std::memcpy(tp.c2, cached_wtaps(h, step, JT, D), sizeof(float2) * (size_t)C::NTW);
-    const long long grid = std::min<long long>(p.total_tiles, h->sm_count);
+    const long long grid = std::min<long long>(p.total_tiles, (long long)h->sm_count * C::CTAS);
     kern<<<(unsigned)grid, C::NWARPS * 32 + 32 * C::NPROD, C::SMEM, st>>>(p, tmap, tp);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
@@ -631,6 +631,9 @@ int launch_ws_j(ddcb200* h, RunParams& p, const float* d_in, long long n_rows, c
         case 8: return launch_ws<D, 8>(h, p, d_in, n_rows, st, step);
         case 16: return launch_ws<D, 16>(h, p, d_in, n_rows, st, step);
         case 32: return launch_ws<D, 32>(h, p, d_in, n_rows, st, step);
+        case 64:
+            if constexpr (D < 16) return launch_ws<D, 64>(h, p, d_in, n_rows, st, step);
+            [[fallthrough]];
         default: return fail(DDCB200_EINVAL, "sliced kernel: unsupported tap-block count %d", jt);
     }
 }
@@ -777,14 +780,15 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         // D = 4 / 8: the same tensor-staged kernel with whole blocks (R = 8 outputs per thread); auto for short filters only,
         // where the rotating-window tile kernel is weakest (see profiles/r1_sweep_taps_decimation.md)
         // measured at N = 2^26 against the tile kernel: D = 4: T = 64 0.090 vs 0.128 ms, T = 128 0.132 vs 0.173; D = 8: T = 64 0.054
-        // vs 0.062, T = 128 0.070 vs 0.083, but T = 256 0.160 vs 0.141 (T * D <= 64 padded taps: whole-row tiles, WSCfg::WHOLE)
+        // vs 0.062, T = 128 0.070 vs 0.083 (T * D <= 64 padded taps: whole-row tiles, WSCfg::WHOLE); with two CTAs per SM
+        // (WSCfg::CTAS) and 64 tap blocks also D = 4: T = 256 0.234 vs 0.274; D = 8: T = 256 0.122 vs 0.141, T = 512 0.229 vs 0.265
         // D = 16: whole-row tiles for the HBM-bound filters (T <= 128: 0.0517 against 0.0524 / 0.0537 ms of the 1-D bulk-copy kernel);
         // longer filters are much slower here than in ddc_kernel_w.cuh (T = 256: 0.312 vs 0.244 ms at 2^28) -- option 11 only
-        const bool small_auto = ((D == 4 || D == 8 || D == 16) && T <= 128);
+        const bool small_auto = (D == 4 && T <= 256) || (D == 8 && T <= 512) || (D == 16 && T <= 128);
         const bool small_d = (D == 4 || D == 8 || D == 16) && (h->force_variant == 11 || (h->force_variant == 0 && small_auto));
-        if (aligned_f32(d_in, in_stride, packed) && Jp <= 32 && T >= D &&
+        if (aligned_f32(d_in, in_stride, packed) && Jp <= (D < 16 ? 64 : 32) && T >= D &&
             (small_d || ((D == 32 || D == 64) && (h->force_variant == 11 || (h->force_variant == 0 && fp32_bound))))) {
-            const int jt = Jp <= 8 ? 8 : (Jp <= 16 ? 16 : 32);
+            const int jt = Jp <= 8 ? 8 : (Jp <= 16 ? 16 : (Jp <= 32 ? 32 : 64));
             const long long n_blocks = (n_samples / (8LL * D)) * 8;         // whole thread-rows of 8 blocks: the tensor map covers exactly these
             long long m_f = n_blocks * D >= T ? (n_blocks * D - T) / D + 1 : 0;   // outputs whose window lies inside them
             if (m_f > M) m_f = M;

@@ -427,7 +427,7 @@ def test_packed_config_full_size(taps_dir):
     assert np.abs(yp[0, 12345: 12345 + 512].cpu().numpy() - ref).max() <= TOL_MAX * scale
 
 
-@pytest.mark.parametrize("d,t", [(4, 64), (4, 128), (8, 128), (8, 40), (4, 20), (8, 64), (16, 100), (16, 256)])
+@pytest.mark.parametrize("d,t", [(4, 64), (4, 128), (8, 128), (8, 40), (4, 20), (8, 64), (16, 100), (16, 256), (4, 256), (8, 500), (8, 256)])
 def test_tensor_staged_kernel_small_decimations(d, t, tmp_path):
     """D = 4 / 8 / 16 through the tensor-staged fast-FIR kernel, 2 streams, ragged length.  Both shared-memory layouts: whole-row
     tiles with the 128-byte swizzle (padded taps <= 64: "row_staged") and per-block tiles with the 32-byte swizzle / plain
@@ -440,7 +440,8 @@ def test_tensor_staged_kernel_small_decimations(d, t, tmp_path):
     ddc.set_option("variant", 11)
     xs = np.stack([synth.digitiser_stream(n, 700 + d + s) for s in range(2)]).astype(np.float32)
     y = ddc.run_tensor(torch.from_numpy(xs).cuda(), 100e6).cpu().numpy()
-    jt = 8 if -(-t // d) <= 8 else (16 if -(-t // d) <= 16 else 32)
+    jp = -(-t // d)
+    jt = 8 if jp <= 8 else (16 if jp <= 16 else (32 if jp <= 32 else 64))
     whole = jt * d <= 64 or (d == 16 and jt == 8)
     assert ("row_staged" if whole else "tensor_staged") in ddc.last_variant, ddc.last_variant
     ref = np.stack([orc.ddc_reference(r, 100e6, tp, d, FS) for r in xs])
