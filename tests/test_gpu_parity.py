@@ -449,6 +449,36 @@ def test_tensor_staged_kernel_small_decimations(d, t, tmp_path):
     assert y.shape == ref.shape and emax <= TOL_MAX and el2 <= TOL_L2, (emax, el2)
 
 
+@pytest.mark.parametrize("d,t", [(4, 64), (4, 256), (8, 64), (8, 512), (16, 128)])
+def test_tensor_staged_kernel_ring_wraparound(d, t, tmp_path):
+    """Long streams through the tensor-staged kernel: every CTA (two per SM at D = 4 / 8) takes several rounds of chunks, so
+    every ring slot is reused and the mbarrier parities flip.  The WHOLE output is compared with the rotating-window tile
+    kernel (option 2, an independent code path), and windows at the head, the middle and the ragged tail with the float64
+    oracle."""
+    from scipy import signal
+
+    n = (1 << 23) + 8 * d * 5 + 3 * d + 4
+    tp = signal.firwin(t, 0.8 / d)
+    ddc = DigitalDownConverter(d, FS, _custom_taps(tmp_path, tp))
+    base = synth.digitiser_stream_fast(n, 77 + d, block=1 << 20).astype(np.float32)
+    xs = torch.from_numpy(np.stack([base, np.roll(base, 12345)])).cuda()
+    y = ddc.run_tensor(xs, 100e6)
+    assert "staged" in ddc.last_variant, ddc.last_variant
+    ddc.set_option("variant", 2)
+    y2 = ddc.run_tensor(xs, 100e6)
+    assert "staged" not in ddc.last_variant, ddc.last_variant
+    scale = float(y2.abs().max())
+    k = 4 if t > 256 else 1
+    assert y.shape == y2.shape and float((y - y2).abs().max()) <= 2 * k * TOL_MAX * scale
+    step = orc.phase_step_cycles(n, 100e6, FS)
+    yh = y[1].cpu().numpy()
+    x1 = np.roll(base, 12345)
+    m = yh.shape[0]
+    for m0 in (0, m // 2 - 100, m - 300):
+        ref = orc.ddc_windowed_f64(x1, m0, 300, step, ddc.ddc_filter_coeffs, d)
+        assert np.abs(yh[m0:m0 + 300] - ref).max() <= k * TOL_MAX * scale, m0
+
+
 def test_warp_specialised_packed_kernel(taps_dir):
     """Option variant=10: unpack warps feeding a float ring, FIR warps consuming it (sequence-word hand-over in shared memory).
     Many chunks per CTA so that every ring slot is reused several times; result against the float32 path."""
