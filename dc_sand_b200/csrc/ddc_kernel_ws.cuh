@@ -20,7 +20,8 @@ namespace ddck {
 template <int D, int JT>
 struct WSCfg {
     static_assert(D == 4 || D == 8 || D == 16 || D == 32 || D == 64, "tensor-staged kernel: D = 32, 64 (sliced) and D = 4, 8, 16 (whole blocks)");
-    static_assert(JT % 2 == 0 && (JT <= 32 || (JT == 64 && D < 16)), "tap blocks: even, at most 32 (halo of four thread-rows); 64 at D = 4 / 8 (eight)");
+    static constexpr int JT_MAX = D == 4 ? 256 : (D == 8 ? 128 : 32);   // the halo grows by two thread-rows per 16 tap blocks
+    static_assert(JT % 2 == 0 && (JT <= 32 || JT % 16 == 0) && JT <= JT_MAX, "tap blocks: even up to 32, then multiples of 16 up to JT_MAX");
     // D = 4 / 8 use the same staging with ONE slice that holds the whole D-sample block: thread-rows of 8 blocks (32 / 64
     // samples) give R = 8 outputs per thread, which the 1-D kernels (128-sample rows) cannot offer at these decimations.
     static constexpr int LPQ = D < 16 ? 1 : D / 16;   // slices per chunk
@@ -50,10 +51,12 @@ struct WSCfg {
     // 6.2 TB/s (D = 8, T = 64).  Longer filters are FP32-bound and keep the per-block tiles, whose window addressing is
     // cheaper (T = 128: 0.132 / 0.071 ms against 0.142 / 0.072 ms at D = 4 / 8).
     static constexpr bool WHOLE = (D < 16 && JT * D <= 64) || (D == 16 && JT <= 8);
-    static constexpr int SLOT_ROWS = JT > 32 ? 40 : 36;              // 32 + up to 4 (8) halo rows
+    // thread-rows of a slot: 32 + the halo, two rows per pass of 16 tap blocks (36 / 40 / 48 / 64 for JT <= 32 / 64 / 128 / 256)
+    static constexpr int SLOT_ROWS = JT <= 32 ? 36 : 32 + 2 * (JT / 16);
+    static constexpr int TILE_ROWS = (SLOT_ROWS + 7) / 8 * 8;        // pitch in lines: a multiple of the swizzle period
     static constexpr int LINE_BYTES = WHOLE ? 128 : DB * 4;          // 128 / 64 / 32 / 16
     static constexpr int NTILE = WHOLE ? (ROW * 4) / 128 : R;        // copies per slot: 1 (D = 4), 2 (D = 8); 8 per-block tiles
-    static constexpr int TILE_BYTES = 40 * LINE_BYTES;               // 36 lines, pitch a multiple of the swizzle period
+    static constexpr int TILE_BYTES = TILE_ROWS * LINE_BYTES;
     static constexpr int SLOT_BYTES = NTILE * TILE_BYTES;
     static constexpr int TX_BYTES = NTILE * SLOT_ROWS * LINE_BYTES;  // bytes landed per slot
     static constexpr int HDR_BYTES = 1024;
@@ -64,7 +67,9 @@ struct WSCfg {
     static constexpr int CTAS = (D == 4 || (D == 8 && !WHOLE)) ? 2 : 1;
     static constexpr int NSLOT_FIT = NSLOT_MAX / CTAS > 16 ? 16 : NSLOT_MAX / CTAS;
     static constexpr int NSLOT = (CTAS == 2 && NSLOT_FIT > 12) ? 12 : NSLOT_FIT;   // 11 at D >= 32
-    static_assert(NSLOT >= NGROUPS + 2 && NSLOT <= 16, "ring size");
+    // nine slots (D = 8 beyond 64 tap blocks, two CTAs per SM): the second producer's four warps then have no slot of read-ahead;
+    // a chunk takes ~30 us of FIR there, so the ~2 us refill is hidden by the other fifteen compute warps of the SM
+    static_assert(NSLOT >= NGROUPS + 1 && NSLOT <= 16, "ring size");
     // per-block tiles: 64-byte swizzle (16-float lines), 32-byte swizzle (8-float lines), none (4-float lines)
     __host__ __device__ static constexpr int swz(int row) { return DB == 16 ? ((row >> 1) & 3) : (DB == 8 ? ((row >> 2) & 1) : 0); }
     static constexpr int CHUNK_ROWS = 32;

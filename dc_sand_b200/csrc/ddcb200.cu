@@ -625,16 +625,20 @@ int launch_ws(ddcb200* h, RunParams& p, const float* d_in, long long n_rows, cud
     return DDCB200_OK;
 }
 
+// tap-block counts beyond 32 come in multiples of 16 (one more pass and two more halo rows each), up to WSCfg::JT_MAX
+template <int D, int JT>
+int launch_ws_from(ddcb200* h, RunParams& p, const float* d_in, long long n_rows, cudaStream_t st, double step, int jt) {
+    if (jt == JT) return launch_ws<D, JT>(h, p, d_in, n_rows, st, step);
+    if constexpr (JT + 16 <= WSCfg<D, 8>::JT_MAX) return launch_ws_from<D, JT + 16>(h, p, d_in, n_rows, st, step, jt);
+    return fail(DDCB200_EINVAL, "tensor-staged kernel: unsupported tap-block count %d at D = %d", jt, D);
+}
+
 template <int D>
 int launch_ws_j(ddcb200* h, RunParams& p, const float* d_in, long long n_rows, cudaStream_t st, double step, int jt) {
     switch (jt) {
         case 8: return launch_ws<D, 8>(h, p, d_in, n_rows, st, step);
         case 16: return launch_ws<D, 16>(h, p, d_in, n_rows, st, step);
-        case 32: return launch_ws<D, 32>(h, p, d_in, n_rows, st, step);
-        case 64:
-            if constexpr (D < 16) return launch_ws<D, 64>(h, p, d_in, n_rows, st, step);
-            [[fallthrough]];
-        default: return fail(DDCB200_EINVAL, "sliced kernel: unsupported tap-block count %d", jt);
+        default: return launch_ws_from<D, 32>(h, p, d_in, n_rows, st, step, jt);
     }
 }
 
@@ -784,11 +788,16 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         // (WSCfg::CTAS) and 64 tap blocks also D = 4: T = 256 0.234 vs 0.274; D = 8: T = 256 0.122 vs 0.141, T = 512 0.229 vs 0.265
         // D = 16: whole-row tiles for the HBM-bound filters (T <= 128: 0.0517 against 0.0524 / 0.0537 ms of the 1-D bulk-copy kernel);
         // longer filters are much slower here than in ddc_kernel_w.cuh (T = 256: 0.312 vs 0.244 ms at 2^28) -- option 11 only
-        const bool small_auto = (D == 4 && T <= 256) || (D == 8 && T <= 512) || (D == 16 && T <= 128);
+        // The kernel pads the filter to 8, 16 or a multiple of 16 tap blocks, the tile kernel to a multiple of its R (16 / 8 at
+        // D = 4 / 8): auto only where the padded work is within 12 % of the tile kernel's (its deficit there: 84-94 % against 99 %).
+        const int jt_ws = Jp <= 8 ? 8 : (Jp + 15) / 16 * 16;
+        const int j_tile = R > 0 ? (Jp + R - 1) / R * R : Jp;
+        const bool pad_ok = jt_ws * 100 <= j_tile * 112;
+        const bool small_auto = (D == 4 && T <= 1024 && pad_ok) || (D == 8 && T <= 1024 && pad_ok) || (D == 16 && T <= 128);
         const bool small_d = (D == 4 || D == 8 || D == 16) && (h->force_variant == 11 || (h->force_variant == 0 && small_auto));
-        if (aligned_f32(d_in, in_stride, packed) && Jp <= (D < 16 ? 64 : 32) && T >= D &&
+        if (aligned_f32(d_in, in_stride, packed) && Jp <= (D == 4 ? 256 : (D == 8 ? 128 : 32)) && T >= D &&
             (small_d || ((D == 32 || D == 64) && (h->force_variant == 11 || (h->force_variant == 0 && fp32_bound))))) {
-            const int jt = Jp <= 8 ? 8 : (Jp <= 16 ? 16 : (Jp <= 32 ? 32 : 64));
+            const int jt = jt_ws;
             const long long n_blocks = (n_samples / (8LL * D)) * 8;         // whole thread-rows of 8 blocks: the tensor map covers exactly these
             long long m_f = n_blocks * D >= T ? (n_blocks * D - T) / D + 1 : 0;   // outputs whose window lies inside them
             if (m_f > M) m_f = M;
