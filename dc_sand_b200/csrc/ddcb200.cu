@@ -607,6 +607,8 @@ int launch_ws(ddcb200* h, RunParams& p, const float* d_in, long long n_rows, cud
     static bool attr_set[64] = {};
     if (h->device < 64 && !attr_set[h->device]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        // two CTAs per SM need the whole shared-memory carve-out (the driver's default follows ONE CTA's request)
+        if (C::CTAS > 1) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set[h->device] = true;
     }
     CUtensorMap tmap;
