@@ -279,6 +279,25 @@ def test_streaming_pushes_equal_one_shot_run(taps_dir):
     assert emax <= TOL_MAX and el2 <= TOL_L2, (emax, el2)
 
 
+@pytest.mark.parametrize("d", [4, 8, 32])
+def test_streaming_small_and_large_decimations(taps_dir, d):
+    """The same ragged pushes at D = 4 / 8 (tensor-staged kernel, two CTAs per SM) and D = 32 (the 53 MHz narrow-band mode):
+    history carry and NCO phase across pushes do not depend on which kernel family serves the chunk."""
+    from dc_sand_b200 import DDCStream
+
+    n = 260_011
+    x = synth.digitiser_stream(n, 56 + d).astype(np.float32)
+    ddc = _ddc(taps_dir, d, "ddc_coeff_53MHz.csv" if d == 32 else "ddc_coeff_107MHz.csv")
+    y_ref = orc.ddc_reference(x, 100e6, ddc.ddc_filter_coeffs, d, FS)
+    with DDCStream(ddc, 100e6, max_chunk=70_000, total_samples=n) as st:
+        cuts = [0, 100, 255, 256, 4347, 40_001, 150_000, 150_016, 259_999, n]
+        y = np.concatenate([st.push(x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])])
+        assert st.position == n and st.pending == n - len(y) * d
+    assert y.shape == y_ref.shape
+    emax, el2 = rel_err(y, y_ref)
+    assert emax <= TOL_MAX and el2 <= TOL_L2, (emax, el2)
+
+
 def test_streaming_device_tensors_many_streams(taps_dir):
     """Device-resident pushes (asynchronous, torch stream) for 3 streams, then a host push on the same session."""
     from dc_sand_b200 import DDCStream
