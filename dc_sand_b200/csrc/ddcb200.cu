@@ -787,13 +787,13 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
     {
         const int Jp = (T + D - 1) / D;
         const bool fp32_bound = 4.0 * T / D > 11.4 * (4.0 + 8.0 / D);
-        // D = 4 / 8: the same tensor-staged kernel with whole blocks (R = 8 outputs per thread); auto for short filters only,
-        // where the rotating-window tile kernel is weakest (see profiles/r1_sweep_taps_decimation.md)
-        // measured at N = 2^26 against the tile kernel: D = 4: T = 64 0.090 vs 0.128 ms, T = 128 0.132 vs 0.173; D = 8: T = 64 0.054
-        // vs 0.062, T = 128 0.070 vs 0.083 (T * D <= 64 padded taps: whole-row tiles, WSCfg::WHOLE); with two CTAs per SM
-        // (WSCfg::CTAS) and 64 tap blocks also D = 4: T = 256 0.234 vs 0.274; D = 8: T = 256 0.122 vs 0.141, T = 512 0.229 vs 0.265
-        // D = 16: whole-row tiles for the HBM-bound filters (T <= 128: 0.0517 against 0.0524 / 0.0537 ms of the 1-D bulk-copy kernel);
-        // longer filters are much slower here than in ddc_kernel_w.cuh (T = 256: 0.312 vs 0.244 ms at 2^28) -- option 11 only
+        // D = 4 / 8 / 16: the same tensor-staged kernel with whole blocks (R = 8 outputs per thread), ddc_kernel_ws.cuh.
+        //   D = 4 / 8, up to 1024 taps: two CTAs per SM (sixteen compute warps; WSCfg::CTAS) -- measured at N = 2^26 against the tile
+        //   kernel: D = 4: T = 64 0.085 vs 0.128 ms, 128 0.126 vs 0.173, 256 0.234 vs 0.274, 512 0.456 vs 0.503, 1024 0.895 vs 0.981;
+        //   D = 8: T = 64 0.054 vs 0.062, 128 0.070 vs 0.083, 256 0.122 vs 0.141, 512 0.229 vs 0.265, 1024 0.449 vs 0.495 (sub-filter
+        //   kernel).  Padded taps <= 64 use whole-row tiles (WSCfg::WHOLE).
+        //   D = 16: whole-row tiles for the HBM-bound filters only (T <= 128: 0.0517 against 0.0524 / 0.0537 ms of the 1-D bulk-copy
+        //   kernel); longer filters are much slower here than in ddc_kernel_w.cuh (T = 256: 0.312 vs 0.244 ms at 2^28): option 11.
         // The kernel pads the filter to 8, 16 or a multiple of 16 tap blocks, the tile kernel to a multiple of its R (16 / 8 at
         // D = 4 / 8): auto only where the padded work is within 12 % of the tile kernel's (its deficit there: 84-94 % against 99 %).
         const int jt_ws = Jp <= 8 ? 8 : (Jp + 15) / 16 * 16;
