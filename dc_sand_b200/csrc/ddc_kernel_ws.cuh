@@ -1,4 +1,6 @@
-// Fast-FIR fused DDC for LARGE decimations (D = 32, 64) -- "kernel WS" (sliced).
+// Tensor-staged fast-FIR fused DDC -- "kernel WS": chunks staged by 5-D TMA tensor copies into swizzled shared-memory tiles.
+// Three uses (WSCfg): SLICED staging for large decimations (D = 32, 64; described first), whole blocks in per-block tiles for
+// D = 4 / 8 (two CTAs per SM), and whole blocks in whole-row tiles for short, HBM-bound filters at D = 4 / 8 / 16.
 //
 // The fast-FIR kernel (ddc_kernel_w.cuh) needs R = 8 outputs per thread so that one tap fetch feeds four FFMA2; with
 // thread-rows of 128 samples that only holds at D = 16 (at D = 32 / 64 the phase-major kernels have R = 4 / 2 and run at
