@@ -52,7 +52,8 @@ struct WSCfg {
     // tiles with 16 / 32-byte lines are TMA-bound there (4.2-4.9 TB/s), the whole-row tiles reach 4.4 TB/s (D = 4, T = 64) and
     // 6.2 TB/s (D = 8, T = 64).  Longer filters are FP32-bound and keep the per-block tiles, whose window addressing is
     // cheaper (T = 128: 0.132 / 0.071 ms against 0.142 / 0.072 ms at D = 4 / 8).
-    static constexpr bool WHOLE = (D < 16 && JT * D <= 64) || (D == 16 && JT <= 8);
+    // (D = 8 with 16 tap blocks: whole-row tiles AND two CTAs, 0.0693 against 0.0702 ms with per-block tiles at T = 128)
+    static constexpr bool WHOLE = (D < 16 && JT * D <= 64) || (D == 16 && JT <= 8) || (D == 8 && JT == 16);
     // thread-rows of a slot: 32 + the halo, two rows per pass of 16 tap blocks (36 / 40 / 48 / 64 for JT <= 32 / 64 / 128 / 256)
     static constexpr int SLOT_ROWS = JT <= 32 ? 36 : 32 + 2 * (JT / 16);
     static constexpr int TILE_ROWS = (SLOT_ROWS + 7) / 8 * 8;        // pitch in lines: a multiple of the swizzle period
@@ -66,7 +67,7 @@ struct WSCfg {
     static constexpr int NSLOT_MAX = (227 * 1024 - HDR_BYTES - 1024) / SLOT_BYTES;
     // D = 4 / 8 with whole-row tiles: TWO CTAs per SM (the slots are small, and 20 warps hide the ring and pipe latencies that
     // 10 cannot: ncu shows the FMA pipe 65 % active and DRAM at 48 % with one CTA); the ring is cut to what two CTAs can hold
-    static constexpr int CTAS = (D == 4 || (D == 8 && !WHOLE)) ? 2 : 1;
+    static constexpr int CTAS = (D == 4 || (D == 8 && JT > 8)) ? 2 : 1;
     static constexpr int NSLOT_FIT = NSLOT_MAX / CTAS > 16 ? 16 : NSLOT_MAX / CTAS;
     static constexpr int NSLOT = (CTAS == 2 && NSLOT_FIT > 12) ? 12 : NSLOT_FIT;   // 11 at D >= 32
     // nine slots (D = 8 beyond 64 tap blocks, two CTAs per SM): the second producer's four warps then have no slot of read-ahead;
