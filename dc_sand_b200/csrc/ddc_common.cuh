@@ -34,7 +34,16 @@ struct RunParams {
     int l2_ahead;                // kernel P: chunks of L2 prefetch distance (0 = off)
     int stagger_cycles;          // start delay of every other compute warp (see ddc_fused_kernel)
     int debug_mode;              // 0 normal; 1 compute only (no TMA, no waits); 2 memory only (no FIR) -- ceilings for tuning
+    unsigned long long cps_magic;// kernel WS: ceil(2^64 / tiles_per_stream), 0 when tiles_per_stream == 1 (see chunk_of)
 };
+
+// (stream, chunk inside the stream) of global chunk gk without a hardware division: floor(gk / cps) = mulhi(gk, ceil(2^64 / cps)),
+// exact while gk * cps < 2^64 (the host checks total_tiles * tiles_per_stream)
+__device__ __forceinline__ void chunk_of(const RunParams& p, long long gk, int& cs, int& cc) {
+    const unsigned long long q = p.cps_magic ? __umul64hi((unsigned long long)gk, p.cps_magic) : (unsigned long long)gk;
+    cs = (int)q;
+    cc = (int)(gk - (long long)q * p.tiles_per_stream);
+}
 
 // ---- NCO: exp(-j 2 pi ph / 2^64) from a 64-bit fixed-point phase ------------------------------------------
 // Quadrant reduction in integers keeps the float conversion exact to 2^-28 cycle (2.3e-8 rad); the remaining

@@ -145,7 +145,8 @@ ddc_fused_ws_kernel(const __grid_constant__ RunParams p, const __grid_constant__
             const int k = round * NG + w;               // local chunk index
             if (k >= n_k) continue;                     // partial last round: this warp has no chunk (consumers skip it too)
             const long long gk = blockIdx.x + (long long)k * gridDim.x;   // global chunk
-            const int cs = (int)(gk / cps), cc = (int)(gk % cps);
+            int cs, cc;
+            chunk_of(p, gk, cs, cc);
             const int slot = sbase + sidx;
             if (elect_one()) {
                 mbar_wait(&empty_bar[slot], par);
@@ -200,6 +201,7 @@ ddc_fused_ws_kernel(const __grid_constant__ RunParams p, const __grid_constant__
         // my positions are the (grp / 2)-th, (grp / 2 + 4)-th, ... of producer grp % 2, but only positions whose chunk exists
         // are staged, so the slot cursor advances per staged position
         const int sbase = C::sub_base(grp % C::NPROD), scnt = C::sub_count(grp % C::NPROD);
+        int scur = grp / C::NPROD;   // slot cursor: index in bits 0-7, mbarrier parity in bit 8; (round 0, slice 0): staged = grp / NPROD < scnt
 
         float2 yprev[R];
 #pragma unroll
@@ -221,17 +223,25 @@ ddc_fused_ws_kernel(const __grid_constant__ RunParams p, const __grid_constant__
             const int pos = (round * LPQ + q) * NG + grp;
             // slot of this position: index among the positions staged by my producer.  In a full round every position is staged;
             // in the partial last round only those of warps < n_k % 8.  Staged positions before `pos` on my producer:
-            int staged;
-            {
-                const int per_slice_full = NG / C::NPROD;                                  // staged per (round, slice) and producer, full rounds
+            // Full rounds advance the cursor by per_slice_full slots per position: kept incrementally (scur) -- a chunk at D = 4
+            // is only ~500 instructions of FIR, and the divisions of the closed form were a tenth of that.  The partial last round
+            // uses the closed form once.
+            constexpr int per_slice_full = NG / C::NPROD;                                  // staged per (round, slice) and producer, full rounds
+            int slot;
+            uint32_t par;
+            if (round < n_rounds - 1) {
+                slot = sbase + (scur & 255);
+                par = (uint32_t)scur >> 8;
+                scur += per_slice_full;
+                if ((scur & 255) >= scnt) scur = (scur - scnt) ^ 256;
+            } else {
                 const int last_cnt = n_k - (n_rounds - 1) * NG;                            // chunks in the last round (1 .. 8)
                 const int par2 = grp % C::NPROD;
                 const int per_slice_last = (last_cnt - par2 + C::NPROD - 1) / C::NPROD;    // warps w < last_cnt with w % 2 == par2
-                if (round < n_rounds - 1) staged = (round * LPQ + q) * per_slice_full + grp / C::NPROD;
-                else staged = (n_rounds - 1) * LPQ * per_slice_full + q * per_slice_last + grp / C::NPROD;
+                const int staged = (n_rounds - 1) * LPQ * per_slice_full + q * per_slice_last + grp / C::NPROD;
+                slot = sbase + staged % scnt;
+                par = (uint32_t)(staged / scnt) & 1u;
             }
-            const int slot = sbase + staged % scnt;
-            const uint32_t par = (uint32_t)(staged / scnt) & 1u;
             spin_until_eq_uni(&slot_seq[slot], pos);
             mbar_wait_uni(&full_bar[slot], par);
             const unsigned char* sbuf = buf + (size_t)slot * C::SLOT_BYTES;
@@ -285,7 +295,8 @@ ddc_fused_ws_kernel(const __grid_constant__ RunParams p, const __grid_constant__
             if (q == LPQ - 1) {
                 // chunk complete: combine the three half-rate sums and hand them to the deferred epilogue
                 const long long gk = blockIdx.x + (long long)k * gridDim.x;
-                const int cs = (int)(gk / cps), cc = (int)(gk % cps);
+                int cs, cc;
+                chunk_of(p, gk, cs, cc);
 #pragma unroll
                 for (int r = 0; r < RH; ++r) {
                     yprev[2 * r] = make_float2(m0a[r].x + m1a[r].x, m0a[r].y + m1a[r].y);

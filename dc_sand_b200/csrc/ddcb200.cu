@@ -615,6 +615,7 @@ int launch_ws(ddcb200* h, RunParams& p, const float* d_in, long long n_rows, cud
         if (C::CTAS > 1) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set[h->device] = true;
     }
+    p.cps_magic = p.tiles_per_stream > 1 ? ~0ull / (unsigned long long)p.tiles_per_stream + 1ull : 0ull;   // chunk_of()
     CUtensorMap tmap;
     int rc = make_slice_tmap(d_in, D, C::WHOLE, C::SLOT_ROWS, n_rows, p.n_streams, p.in_stride, &tmap);
     if (rc) return rc;
@@ -807,6 +808,8 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
             const long long n_blocks = (n_samples / (8LL * D)) * 8;         // whole thread-rows of 8 blocks: the tensor map covers exactly these
             long long m_f = n_blocks * D >= T ? (n_blocks * D - T) / D + 1 : 0;   // outputs whose window lies inside them
             if (m_f > M) m_f = M;
+            // chunk_of() divides by multiplication: exact while total chunks x chunks per stream < 2^64
+            if ((double)((m_f + 255) / 256) * (double)((m_f + 255) / 256) * (double)n_streams >= 1.8e19) m_f = 0;
             if (m_f > 0) {
                 const long long m_all = p.n_out;
                 p.n_out = m_f;
