@@ -95,6 +95,21 @@ __device__ __forceinline__ void tma_load_5d(void* dst_smem, const CUtensorMap* t
         : "memory");
 }
 
+// Epilogue with a warp-uniform shortcut in front of the branch-free w_epilogue (ddc_kernel_w.cuh): nothing at all when the stores
+// are disabled (slices 1 .. LPQ-1 of a chunk, first chunk of a warp).  (A second shortcut -- plain 16-byte stores without the
+// per-output predicates when every lane has all R outputs -- was tried: both store paths alive at once cost 300 bytes of spills.)
+// Sliced kernels only (LPQ > 1): with one slice per chunk the shortcut would only ever skip a warp's first chunk, and the branch
+// costs the register-capped two-CTA kernels 300 bytes of spills.
+template <int R, int LPQ>
+__device__ __forceinline__ void ws_epilogue(const float2 (&y)[R], const float2 (&rot_thr)[R], unsigned long long chunk_phase,
+                                            long long m0, float2* o, long long nout) {
+    if constexpr (LPQ > 1) {
+        if (nout != 0) w_epilogue<R>(y, rot_thr, chunk_phase, m0, o, nout);   // warp-uniform
+    } else {
+        w_epilogue<R>(y, rot_thr, chunk_phase, m0, o, nout);
+    }
+}
+
 // Work items of a CTA are POSITIONS: position = (round * LPQ + q) * 8 + w  <->  slice q of the chunk that compute warp w
 // handles in its round-th turn (local chunk index round * 8 + w).  Producer p stages positions = p (mod 2) in order, into
 // its own sub-ring; warp w consumes positions w, w + 8, ...: consumption order matches staging order.
@@ -257,7 +272,7 @@ ddc_fused_ws_kernel(const __grid_constant__ RunParams p, const __grid_constant__
             {   // first pass of the slice; it carries the previous chunk's epilogue (stores enabled only once per chunk)
                 float4 w[NW];
                 load_window(w, sbuf, g, 0);
-                w_epilogue<R>(yprev, rot_thr, p.phase0_fx + (unsigned long long)prev_cc * chunk_dph, prev_m0, prev_o,
+                ws_epilogue<R, LPQ>(yprev, rot_thr, p.phase0_fx + (unsigned long long)prev_cc * chunk_dph, prev_m0, prev_o,
                               q == 0 ? prev_nout : 0);
                 w_fir_pg<D, JP, R>(w, tp, m0a, m1a, m2a);
                 pgv = 1;
@@ -311,7 +326,7 @@ ddc_fused_ws_kernel(const __grid_constant__ RunParams p, const __grid_constant__
             }
           }
         }
-        w_epilogue<R>(yprev, rot_thr, p.phase0_fx + (unsigned long long)prev_cc * chunk_dph, prev_m0, prev_o, prev_nout);
+        ws_epilogue<R, LPQ>(yprev, rot_thr, p.phase0_fx + (unsigned long long)prev_cc * chunk_dph, prev_m0, prev_o, prev_nout);
     }
 }
 
