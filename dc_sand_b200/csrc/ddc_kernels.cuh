@@ -89,6 +89,28 @@ __global__ void unpack10_rows_kernel(const uint8_t* __restrict__ in, long long i
         make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
 }
 
+// Inverse of the unpack stage, for test-vector generation in HBM (ddcb200_pack10): float32 samples are rounded, clipped to
+// [-512, 511] and written in the transport format, 4 samples -> 5 bytes, rows of [streams].
+__global__ void pack10_rows_kernel(const float* __restrict__ in, long long in_stride, long long n_groups, uint8_t* __restrict__ out,
+                                   long long out_stride_bytes) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const float* x = in + (long long)blockIdx.y * in_stride + g * 4;
+    uint32_t u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int v = __float2int_rn(x[k]);
+        v = v < -512 ? -512 : (v > 511 ? 511 : v);
+        u[k] = (uint32_t)v & 0x3FFu;
+    }
+    uint8_t* b = out + (long long)blockIdx.y * out_stride_bytes + g * 5;
+    b[0] = (uint8_t)(u[0] >> 2);
+    b[1] = (uint8_t)(((u[0] & 0x3u) << 6) | (u[1] >> 4));
+    b[2] = (uint8_t)(((u[1] & 0xFu) << 4) | (u[2] >> 6));
+    b[3] = (uint8_t)(((u[2] & 0x3Fu) << 2) | (u[3] >> 8));
+    b[4] = (uint8_t)(u[3] & 0xFFu);
+}
+
 // Stage kernels: the reference exposes its three stages as separate methods (ddc.py:51-66, 85-100, 102-119).  The fused
 // kernels above are what run() uses; these exist so that the stage methods of the drop-in class also execute on the GPU.
 __global__ void mix_kernel(const float* __restrict__ x, const float2* __restrict__ cw, float2* __restrict__ out, long long n) {

@@ -56,6 +56,21 @@ struct DeviceGuard {
     }
 };
 
+// Strided copy that never hands the driver a pitch it may reject (cudaDeviceProp::memPitch is 2^31 - 1 bytes): one row, or
+// rows that happen to be contiguous, go as ONE flat copy; rows with a pitch beyond the limit go one by one.
+cudaError_t copy_rows_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows,
+                            cudaMemcpyKind kind, cudaStream_t st) {
+    if (rows == 0 || width == 0) return cudaSuccess;
+    if (rows == 1 || (dpitch == width && spitch == width)) return cudaMemcpyAsync(dst, src, width * rows, kind, st);
+    constexpr size_t kMaxPitch = 0x7fffffffull;
+    if (dpitch <= kMaxPitch && spitch <= kMaxPitch) return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, st);
+    for (size_t r = 0; r < rows; ++r) {
+        cudaError_t e = cudaMemcpyAsync(static_cast<char*>(dst) + r * dpitch, static_cast<const char*>(src) + r * spitch, width, kind, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 }  // namespace
 
 struct ddcb200 {
@@ -100,6 +115,7 @@ struct ddcb200 {
     int copy_threads = 4;
     float* d_unpack_ws = nullptr;          // float32 workspace of the two-launch packed path (unpack, then a float32 kernel)
     size_t unpack_ws_cap = 0;
+    cudaEvent_t unpack_ev = nullptr;       // end of the last kernel that read the workspace (calls may come on different streams)
     ddcb200_c64* h_ostage[kBufs] = {};   // pinned landing buffers for the complex128 host path (one per chunk buffer)
     size_t ostage_cap = 0;
     std::vector<float2> wq_cache;   // same for the small-decimation kernel
@@ -108,6 +124,19 @@ struct ddcb200 {
 };
 
 namespace {
+
+// Host-path calls queue work on three streams and read / write the caller's host buffers asynchronously: whatever way such a
+// call ends (also a mid-pipeline error), nothing may still be in flight when it returns -- the caller is free to release the
+// buffers.  Synchronising idle streams costs nothing on the success path.
+struct DrainGuard {
+    ddcb200* h;
+    explicit DrainGuard(ddcb200* hh) : h(hh) {}
+    ~DrainGuard() {
+        cudaStreamSynchronize(h->copy_in);
+        cudaStreamSynchronize(h->stream);
+        cudaStreamSynchronize(h->copy_out);
+    }
+};
 
 // c[k] = taps[T-1-k]/sum * exp(-j 2 pi k step), float64 -> float32; zero padded to n_pad
 void make_ctaps(const ddcb200* h, double step, int n_pad, float2* out) {
@@ -561,18 +590,16 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled get_encode_tiled() {
-    static PFN_encodeTiled fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // magic static: initialised exactly once, thread-safe (handles on different devices are driven from different threads)
+    static const PFN_encodeTiled fn = [] {
         void* sym = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
             qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_encodeTiled>(sym);
-        else
-            cudaGetLastError();
-    }
+            return reinterpret_cast<PFN_encodeTiled>(sym);
+        cudaGetLastError();
+        return static_cast<PFN_encodeTiled>(nullptr);
+    }();
     return fn;
 }
 
@@ -760,6 +787,7 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         const size_t need = (size_t)pitch * (size_t)n_streams;
         if (need > h->unpack_ws_cap) {
             CUDA_TRY(cudaStreamSynchronize(st));   // a previous launch may still read the old workspace
+            if (h->unpack_ev) CUDA_TRY(cudaEventSynchronize(h->unpack_ev));
             if (h->d_unpack_ws) cudaFree(h->d_unpack_ws);
             h->d_unpack_ws = nullptr;
             h->unpack_ws_cap = 0;
@@ -769,12 +797,17 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
             }
             h->unpack_ws_cap = need;
         }
+        // the workspace is shared by every call on this handle, whatever stream it comes on: order this unpack behind the
+        // last kernel that read it
+        if (!h->unpack_ev) CUDA_TRY(cudaEventCreateWithFlags(&h->unpack_ev, cudaEventDisableTiming));
+        else CUDA_TRY(cudaStreamWaitEvent(st, h->unpack_ev, 0));
         const long long groups = n_samples / 4;
         dim3 grid((unsigned)((groups + 255) / 256), (unsigned)n_streams);
         unpack10_rows_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint8_t*>(d_in), in_stride, groups, h->d_unpack_ws, pitch);
         CUDA_TRY(cudaGetLastError());
         h->launches++;
         int rc2 = run_device(h, h->d_unpack_ws, false, n_samples, n_streams, pitch, step, sample_offset, d_out, out_stride, st, m_limit);
+        CUDA_TRY(cudaEventRecord(h->unpack_ev, st));
         if (rc2) return rc2;
         h->last_variant = "unpack10+" + h->last_variant;
         return DDCB200_OK;
@@ -940,6 +973,7 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
 
 int ensure_chunks(ddcb200* h, size_t in_bytes, size_t out_elems) {
     if (in_bytes > h->chunk_in_cap) {
+        h->chunk_in_cap = 0;   // only valid again once every buffer has been allocated
         for (int i = 0; i < ddcb200::kBufs; ++i) {
             if (h->d_chunk_in[i]) cudaFree(h->d_chunk_in[i]);
             h->d_chunk_in[i] = nullptr;
@@ -948,6 +982,7 @@ int ensure_chunks(ddcb200* h, size_t in_bytes, size_t out_elems) {
         h->chunk_in_cap = in_bytes;
     }
     if (out_elems > h->chunk_out_cap) {
+        h->chunk_out_cap = 0;
         for (int i = 0; i < ddcb200::kBufs; ++i) {
             if (h->d_chunk_out[i]) cudaFree(h->d_chunk_out[i]);
             h->d_chunk_out[i] = nullptr;
@@ -1055,6 +1090,7 @@ int run_host(ddcb200* h, const void* h_in, bool packed, int64_t n_samples, int64
     const size_t in_row_bytes = (size_t)in_chunk_samples / in_elem_den * in_elem_bytes_num;
     int rc = ensure_chunks(h, in_row_bytes * (size_t)n_streams + 64, (size_t)m_chunk * (size_t)n_streams);
     if (rc) return rc;
+    DrainGuard drain(h);
     const bool pageable_in = h->copy_threads > 0 && is_pageable(h_in);
     if (h_out128) {
         if (n_streams != 1) return fail(DDCB200_EINVAL, "complex128 host output is for one stream per call");
@@ -1093,8 +1129,8 @@ int run_host(ddcb200* h, const void* h_in, bool packed, int64_t n_samples, int64
             rc = staged_h2d(h, h->d_chunk_in[b], reinterpret_cast<const char*>(h_in) + src_off, row_bytes, h->copy_in);
             if (rc) return rc;
         } else {
-            CUDA_TRY(cudaMemcpy2DAsync(h->d_chunk_in[b], in_row_bytes, reinterpret_cast<const char*>(h_in) + src_off, src_pitch,
-                                       row_bytes, (size_t)n_streams, cudaMemcpyHostToDevice, h->copy_in));
+            CUDA_TRY(copy_rows_async(h->d_chunk_in[b], in_row_bytes, reinterpret_cast<const char*>(h_in) + src_off, src_pitch,
+                                     row_bytes, (size_t)n_streams, cudaMemcpyHostToDevice, h->copy_in));
         }
         CUDA_TRY(cudaEventRecord(h->ev_in[b], h->copy_in));
         CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
@@ -1118,9 +1154,9 @@ int run_host(ddcb200* h, const void* h_in, bool packed, int64_t n_samples, int64
             pend_mc = mc;
             pend_b = b;
         } else {
-            CUDA_TRY(cudaMemcpy2DAsync(h_out + m0, (size_t)out_stride * sizeof(ddcb200_c64), h->d_chunk_out[b],
-                                       (size_t)m_chunk * sizeof(ddcb200_c64), (size_t)mc * sizeof(ddcb200_c64), (size_t)n_streams,
-                                       cudaMemcpyDeviceToHost, h->copy_out));
+            CUDA_TRY(copy_rows_async(h_out + m0, (size_t)out_stride * sizeof(ddcb200_c64), h->d_chunk_out[b],
+                                     (size_t)m_chunk * sizeof(ddcb200_c64), (size_t)mc * sizeof(ddcb200_c64), (size_t)n_streams,
+                                     cudaMemcpyDeviceToHost, h->copy_out));
             CUDA_TRY(cudaEventRecord(h->ev_out[b], h->copy_out));
         }
     }
@@ -1213,6 +1249,7 @@ void ddcb200_destroy(ddcb200_t* h) {
     for (int i = 0; i < ddcb200::kBufs; ++i)
         if (h->h_ostage[i]) cudaFreeHost(h->h_ostage[i]);
     if (h->d_unpack_ws) cudaFree(h->d_unpack_ws);
+    if (h->unpack_ev) cudaEventDestroy(h->unpack_ev);
     for (int i = 0; i < ddcb200::kBufs; ++i) {
         if (h->d_chunk_in[i]) cudaFree(h->d_chunk_in[i]);
         if (h->d_chunk_out[i]) cudaFree(h->d_chunk_out[i]);
@@ -1251,6 +1288,22 @@ int ddcb200_unpack10(ddcb200_t* h, const uint8_t* d_in, int64_t n_samples, int16
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
     const long long groups = n_samples / 4;
     unpack10_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(d_in, groups, o16, of32);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return DDCB200_OK;
+}
+
+int ddcb200_pack10(ddcb200_t* h, const float* d_in, int64_t n_samples, int64_t n_streams, int64_t in_stride, uint8_t* d_out,
+                   int64_t out_stride_bytes, void* cuda_stream) {
+    if (!h || !d_in || !d_out) return fail(DDCB200_EINVAL, "pack10: bad arguments");
+    if (n_samples <= 0 || (n_samples % 4) || n_streams <= 0 || n_streams > 65535)
+        return fail(DDCB200_EINVAL, "pack10: n_samples must be a positive multiple of 4, 1 .. 65535 streams");
+    if (in_stride < n_samples || out_stride_bytes < n_samples / 4 * 5) return fail(DDCB200_EINVAL, "pack10: strides shorter than a row");
+    DeviceGuard g(h->device);
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    const long long groups = n_samples / 4;
+    dim3 grid((unsigned)((groups + 255) / 256), (unsigned)n_streams);
+    pack10_rows_kernel<<<grid, 256, 0, st>>>(d_in, in_stride, groups, d_out, out_stride_bytes);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
     return DDCB200_OK;
@@ -1513,8 +1566,8 @@ int stream_step(ddcb200_session* s, int64_t n, ddcb200_c64* d_out, int64_t out_s
     }
     const int64_t used = m * D, rest = have - used;
     if (rest > 0 && used > 0)
-        CUDA_TRY(cudaMemcpy2DAsync(s->work[s->cur ^ 1], (size_t)s->pitch, s->work[s->cur] + s->bytes(used), (size_t)s->pitch,
-                                   s->bytes(rest), (size_t)s->n_streams, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(copy_rows_async(s->work[s->cur ^ 1], (size_t)s->pitch, s->work[s->cur] + s->bytes(used), (size_t)s->pitch,
+                                 s->bytes(rest), (size_t)s->n_streams, cudaMemcpyDeviceToDevice, st));
     if (used > 0) s->cur ^= 1;
     s->carry = rest;
     s->abs0 += used;
@@ -1575,8 +1628,8 @@ int session_push_dev(ddcb200_session_t* s, const void* d_in, bool packed, int64_
     if (m > 0 && (!d_out || out_stride < m)) return fail(DDCB200_EINVAL, "session_push: output too small for %lld outputs", (long long)m);
     DeviceGuard g(s->h->device);
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : s->h->stream;
-    CUDA_TRY(cudaMemcpy2DAsync(s->work[s->cur] + s->bytes(s->carry), (size_t)s->pitch, d_in, (size_t)in_stride * (packed ? 1 : 4),
-                               s->bytes(n_samples), (size_t)s->n_streams, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(copy_rows_async(s->work[s->cur] + s->bytes(s->carry), (size_t)s->pitch, d_in, (size_t)in_stride * (packed ? 1 : 4),
+                             s->bytes(n_samples), (size_t)s->n_streams, cudaMemcpyDeviceToDevice, st));
     int rc = stream_step(s, n_samples, d_out, out_stride, n_out, st);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(s->ev_user, st));
@@ -1593,6 +1646,7 @@ int session_push_host(ddcb200_session_t* s, const void* h_in, bool packed, int64
     if (m_total > 0 && (!h_out || out_stride < m_total)) return fail(DDCB200_EINVAL, "session_push_host: output too small");
     ddcb200* h = s->h;
     DeviceGuard g(h->device);
+    DrainGuard drain(h);
     // Pieces of max_chunk samples, two work buffers deep: the H2D copy of piece i + 1 (copy_in stream) runs under the
     // kernel of piece i (compute stream), the D2H copy of its outputs on copy_out.
     if (s->user_pending) {   // an asynchronous device push may still be using the work buffers on the caller's stream
@@ -1607,9 +1661,9 @@ int session_push_host(ddcb200_session_t* s, const void* h_in, bool packed, int64
         const int64_t n = std::min<int64_t>(s->max_chunk, n_samples - done);
         const int b = s->cur;
         if (rec_k[b]) CUDA_TRY(cudaStreamWaitEvent(h->copy_in, s->ev_k[b], 0));     // last kernel / tail copy reading work[b]
-        CUDA_TRY(cudaMemcpy2DAsync(s->work[b] + s->bytes(s->carry), (size_t)s->pitch,
-                                   reinterpret_cast<const unsigned char*>(h_in) + s->bytes(done), src_pitch, s->bytes(n),
-                                   (size_t)s->n_streams, cudaMemcpyHostToDevice, h->copy_in));
+        CUDA_TRY(copy_rows_async(s->work[b] + s->bytes(s->carry), (size_t)s->pitch,
+                                 reinterpret_cast<const unsigned char*>(h_in) + s->bytes(done), src_pitch, s->bytes(n),
+                                 (size_t)s->n_streams, cudaMemcpyHostToDevice, h->copy_in));
         CUDA_TRY(cudaEventRecord(s->ev_in[b], h->copy_in));
         CUDA_TRY(cudaStreamWaitEvent(h->stream, s->ev_in[b], 0));
         if (rec_out[b]) CUDA_TRY(cudaStreamWaitEvent(h->stream, s->ev_out[b], 0));  // dout[b] has been copied out
@@ -1620,9 +1674,9 @@ int session_push_host(ddcb200_session_t* s, const void* h_in, bool packed, int64
         rec_k[b] = true;
         if (m > 0) {
             CUDA_TRY(cudaStreamWaitEvent(h->copy_out, s->ev_k[b], 0));
-            CUDA_TRY(cudaMemcpy2DAsync(h_out + m_done, (size_t)out_stride * sizeof(ddcb200_c64), s->dout[b],
-                                       (size_t)s->out_cap * sizeof(ddcb200_c64), (size_t)m * sizeof(ddcb200_c64),
-                                       (size_t)s->n_streams, cudaMemcpyDeviceToHost, h->copy_out));
+            CUDA_TRY(copy_rows_async(h_out + m_done, (size_t)out_stride * sizeof(ddcb200_c64), s->dout[b],
+                                     (size_t)s->out_cap * sizeof(ddcb200_c64), (size_t)m * sizeof(ddcb200_c64),
+                                     (size_t)s->n_streams, cudaMemcpyDeviceToHost, h->copy_out));
             CUDA_TRY(cudaEventRecord(s->ev_out[b], h->copy_out));
             rec_out[b] = true;
         }

@@ -110,3 +110,31 @@ def generate_carrier_wave_gpu(cw_scale: float, freq: float, sampling_frequency: 
         "ddcb200_cwg",
     )
     return out[0] if n_streams is None else out
+
+
+def pack10_gpu(x, out=None):
+    """Digitiser transport format built in HBM (ddcb200_pack10): float32 CUDA tensor [n] or [streams, n] (n % 4 == 0,
+    contiguous rows) -> uint8 [.., 5 n / 4]; samples are rounded to nearest and clipped to [-512, 511].  The inverse of
+    DigitalDownConverter._decode_8bit_to_10bit_to_float_data, for packed test vectors that never touch the host."""
+    import torch
+
+    from . import _lib
+    from .ddc import _torch_stream
+
+    one_d = x.dim() == 1
+    x2 = x.unsqueeze(0) if one_d else x
+    if not x2.is_cuda or x2.dim() != 2 or x2.dtype != torch.float32 or x2.stride(1) != 1 or x2.shape[1] % 4:
+        raise ValueError("pack10_gpu needs float32 CUDA rows with contiguous samples, n % 4 == 0")
+    s, n = x2.shape
+    if out is None:
+        out = torch.empty((s, n // 4 * 5), dtype=torch.uint8, device=x.device)
+    out2 = out.unsqueeze(0) if out.dim() == 1 else out
+    if out2.shape != (s, n // 4 * 5) or out2.dtype != torch.uint8 or out2.stride(1) != 1:
+        raise ValueError("out must be uint8 [streams, 5 n / 4] with contiguous rows")
+    dev = x.device.index
+    _lib.check(
+        _lib.load().ddcb200_pack10(_generator_handle(dev), x2.data_ptr(), n, s, x2.stride(0), out2.data_ptr(), out2.stride(0),
+                                   _torch_stream(torch, x.device)),
+        "ddcb200_pack10",
+    )
+    return out2[0] if one_d else out2

@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import logging
+import weakref
 
 import numpy as np
 from numpy import genfromtxt
@@ -42,6 +43,7 @@ class DigitalDownConverter:
         self.device = int(device)
         self._handle = None
         self._handle_key = None
+        self._sessions = weakref.WeakSet()   # open DDCStream sessions: they hold the native handle and its (T, D) geometry
 
     # ------------------------------------------------------------------------------------------------ taps
     def _import_ddc_filter_coeffs(self, filename: str = "ddc_filter_coeffs_107.csv"):
@@ -55,12 +57,16 @@ class DigitalDownConverter:
     def _get_handle(self):
         """Create (or refresh, if the public attributes were changed) the native handle."""
         lib = _lib.load()
+        if int(self.decimation_factor) != self.decimation_factor or int(self.decimation_factor) <= 0:
+            raise ValueError(f"decimation_factor must be a positive integer, got {self.decimation_factor!r}")
         taps = np.ascontiguousarray(self.ddc_filter_coeffs, dtype=np.float64).reshape(-1)
         key = (int(self.decimation_factor), taps.tobytes(), self.device)
         if self._handle is not None and key == self._handle_key:
             return self._handle
-        if int(self.decimation_factor) != self.decimation_factor or int(self.decimation_factor) <= 0:
-            raise ValueError(f"decimation_factor must be a positive integer, got {self.decimation_factor!r}")
+        if self._handle is not None and any(s._s is not None for s in self._sessions):
+            # a session's carry, pitch and output capacity were sized for the old taps / decimation
+            raise RuntimeError("decimation_factor / ddc_filter_coeffs changed while a DDCStream of this object is open; "
+                               "close the stream first")
         if self._handle is None:
             h = C.c_void_p()
             _lib.check(
@@ -76,6 +82,8 @@ class DigitalDownConverter:
         return self._handle
 
     def close(self):
+        for s in list(getattr(self, "_sessions", ())):   # sessions dereference the handle: they go first
+            s.close()
         if getattr(self, "_handle", None) is not None:
             _lib.load().ddcb200_destroy(self._handle)
             self._handle = None
@@ -128,7 +136,16 @@ class DigitalDownConverter:
             # the reference fails in _mix with a broadcasting ValueError for anything but 1-D input
             raise ValueError(f"operands could not be broadcast together: input_data must be 1-D, got shape {x.shape}")
         if np.iscomplexobj(x):
-            raise ValueError("input_data must be real-valued digitiser samples")
+            # The reference multiplies whatever it is given by the carrier (ddc.py:66), so complex input works there; the
+            # operator is linear, so here the real and imaginary parts go through the kernel as two streams of one batch.
+            parts = np.stack([x.real, x.imag]).astype(np.float32)
+            yb = self.run_batch(parts, center_freq, sample_offset=sample_offset, total_samples=total_samples) \
+                if parts.shape[1] >= len(self.ddc_filter_coeffs) else \
+                np.stack([self.run(p, center_freq, sample_offset, total_samples).astype(np.complex64) for p in parts])
+            return yb[0].astype(np.complex128) + 1j * yb[1].astype(np.complex128)
+        # Any real dtype the reference accepts (int8 .. float64) is converted to float32, the device's sample type: exact for
+        # digitiser data (<= 16-bit integers); float64 input is rounded to float32 where the reference would keep it (6e-8
+        # relative, far inside the parity tolerance)
         x = np.ascontiguousarray(x, dtype=np.float32)
         n = x.shape[0]
         step = self.phase_step(n if total_samples is None else int(total_samples), center_freq)

@@ -33,12 +33,14 @@ class DDCStream:
         opener = _lib.load().ddcb200_session_open_packed10 if self.packed else _lib.load().ddcb200_session_open
         _lib.check(opener(ddc._get_handle(), self.n_streams, self.max_chunk, self.phase_step, C.byref(s)), "ddcb200_session_open")
         self._s = s
+        ddc._sessions.add(self)   # ddc.close() closes me first; ddc refuses to change taps / decimation while I am open
 
     # ------------------------------------------------------------------------------------------------------------
     def close(self) -> None:
         if getattr(self, "_s", None) is not None:
             _lib.load().ddcb200_session_close(self._s)
             self._s = None
+            self.ddc._sessions.discard(self)
 
     def __del__(self):  # pragma: no cover
         try:

@@ -89,6 +89,12 @@ int ddcb200_run_packed10(ddcb200_t* handle, const uint8_t* d_in, int64_t n_sampl
 int ddcb200_unpack10(ddcb200_t* handle, const uint8_t* d_in, int64_t n_samples, int16_t* d_out_i16,
                      float* d_out_f32, void* cuda_stream);
 
+/* Inverse of the unpack stage for test vectors built in HBM (the reference has neither a packer nor an unpacker, only the
+ * stub ddc.py:68-83; the format is this library's, see above): float32 samples are rounded to nearest, clipped to
+ * [-512, 511] and written 4 samples -> 5 bytes.  Rows of n_streams; strides in float32 elements / bytes. */
+int ddcb200_pack10(ddcb200_t* handle, const float* d_in, int64_t n_samples, int64_t n_streams, int64_t in_stride,
+                   uint8_t* d_out, int64_t out_stride_bytes, void* cuda_stream);
+
 /* N < T corner of the reference: scipy swaps the operands, so run() returns
  *     y[i] = (1/sum(taps)) * sum_n mix[n] * taps[i*D' ... ]   -- precisely: full[i] = sum_n mix[n]*taps[i+N-1-n],
  * i = 0..T-N, then [0::D].  Kept for drop-in fidelity (ddc.py:98 with len(mix) < len(taps)); single stream. */
