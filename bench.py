@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """Benchmark of the fused digital down-converter (BASELINE.json: "DDC input Gsamples/s and % of HBM roofline").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c5]     (sweep: tools/sweep.py)
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c5] [--no-extra]
 
 One "step" = one pass of the hot path (NCO mix -> FIR -> decimate) over one batch of synthetic digitiser samples.
-  N = 1  : BASELINE configs[1]  "single L-band stream (1712 MSPS), 2^28 samples, 256 taps, decimation 16".
-  N > 1  : launched with torch.distributed.run, one rank per GPU; every rank processes 16 streams x 2^24 samples
-           (= 2^28 samples per GPU, so N = 8 is BASELINE configs[4]: 128 streams sharded by stream); weak scaling,
-           no collective on the data path; device-timed, max over ranks.
-`value` is device-resident throughput (inputs already in HBM); `e2e` is the same metric through the reference-
-facing host API (pinned host buffers, H2D and D2H inside the timed region).  `--impl reference` times the CPU
-restatement of the reference (oracle/ddc_oracle.py, the reference itself cannot travel to the GPU box) on all
-host cores.  Prints ONE JSON line.
+  N = 1  : BASELINE configs[1]  "single L-band stream (1712 MSPS), 2^28 samples, 256 taps, decimation 16" is the headline
+           `value`; the same line carries the other configs measured in the same run under `extra`: `c3` (64 packed
+           streams), `sweep` / `sweep_packed` (the 25 tap x decimation cells), `c5_g1` (the 128-stream workload of
+           configs[4] on one GPU: the G = 1 point of the strong-scaling curve) and `e2e_run_api` (the drop-in
+           DigitalDownConverter.run() on a pageable NumPy array, complex128 out).
+  N > 1  : launched with torch.distributed.run, one rank per GPU; BASELINE configs[4]: the SAME 128 streams x 2^24 samples
+           at every N, 128 / N per GPU (strong scaling), no collective on the data path; device-timed, max over ranks.
+Inputs are generated in HBM by the library's own test-vector generator (ddcb200_cwg, digitiser model) and, for the e2e leg,
+copied once to pinned host memory.  `value` is device-resident throughput (inputs already in HBM); `e2e` is the same metric
+through the reference-facing host API (pinned host buffers, H2D and D2H inside the timed region).  Every rank checks two
+512-output windows of what the timed launches produced against the float64 windowed oracle (`parity_max_err`, outside the
+timed region).  `--impl reference` times the CPU restatement of the reference (oracle/ddc_oracle.py; the reference itself
+cannot travel to the GPU box) on all host cores.  Prints ONE JSON line.
 """
 from __future__ import annotations
 
@@ -154,18 +159,6 @@ def bind_to_gpu_numa(index: int):
     return None
 
 
-def make_input(n_streams: int, n: int, rank: int, packed: bool):
-    """Synthetic tone + noise, 10-bit quantised. Large arrays reuse a 2^22-sample block per stream (rolled)."""
-    from dc_sand_b200 import synth
-
-    rows = []
-    for s in range(n_streams):
-        seed = 1234 + rank * 4096 + s
-        v = synth.digitiser_stream_fast(n, seed, block=min(n, 1 << 22)) if n > (1 << 22) else synth.digitiser_stream(n, seed)
-        rows.append(synth.pack10(v) if packed else v.astype(np.float32))
-    return np.stack(rows)
-
-
 # ----------------------------------------------------------------------------------------------------------------
 # CPU arms
 # ----------------------------------------------------------------------------------------------------------------
@@ -260,18 +253,55 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+TOTAL_STREAMS_C5 = 128          # BASELINE configs[4]: 64 antennas x 2 polarisations
+
+
 def workload_name(args):
     if args.workload == "c3":
         return "64 streams x 2^24 packed 10-bit samples, 256 taps, decimation 16 (BASELINE configs[2])"
     if args.gpus == 1 and args.workload == "c2":
         return "single L-band stream (1712 MSPS), 2^28 float32 samples, 256 taps, decimation 16 (BASELINE configs[1])"
-    return (f"{16 * args.gpus} streams x 2^24 float32 samples sharded by stream over {args.gpus} GPU(s), 16 per GPU, "
-            "256 taps, decimation 16 (BASELINE configs[4] at 8 GPUs)")
+    per = TOTAL_STREAMS_C5 // max(args.gpus, 1)
+    return (f"{TOTAL_STREAMS_C5} streams x 2^24 float32 samples sharded by stream over {args.gpus} GPU(s), {per} per GPU, "
+            "256 taps, decimation 16 (BASELINE configs[4])")
 
 
 # ----------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------
+def roofline_of(n_streams, n, m, t, d, packed, kern_s, variant, hbm_peak, peak_src, traffic=None):
+    """algorithmic bytes = (B_in + 8 / D) per input sample, direct-form flops = 4 T per output; the fast-FIR
+    kernels EXECUTE 3/4 of those multiplies (plus one packed subtraction per window sample, not counted).  `bound` is the
+    floor that binds: max(bytes / HBM peak, executed flops / CUDA-core FP32 peak); `floor_frac` = t_floor / t."""
+    b_in = 1.25 if packed else 4.0
+    alg_bytes = n_streams * n * (b_in + 8.0 / d)
+    flops = 4.0 * t * m * n_streams
+    exec_flops = flops * (0.75 if "fast_fir" in variant else 1.0)
+    t_hbm = alg_bytes / (hbm_peak * 1e9)
+    t_fp32 = exec_flops / (FP32_PEAK_TFLOPS * 1e12)
+    achieved = alg_bytes / kern_s / 1e9
+    return {
+        "bound": "hbm" if t_hbm >= t_fp32 else "fp32",
+        "achieved": achieved,
+        "peak": hbm_peak,
+        "unit": "GB/s",
+        "frac": achieved / hbm_peak,
+        "traffic": traffic,
+        "peak_source": peak_src,
+        "frac_of_nominal_8TBs": achieved / 8000.0,
+        "floor_frac": max(t_hbm, t_fp32) / kern_s,
+        "t_floor_hbm_ms": t_hbm * 1e3,
+        "t_floor_fp32_executed_ms": t_fp32 * 1e3,
+        "fp32_direct_form_tflops": flops / kern_s / 1e12,
+        "fp32_executed_tflops": exec_flops / kern_s / 1e12,
+        "fp32_executed_frac": exec_flops / kern_s / 1e12 / FP32_PEAK_TFLOPS,
+        "fp32_peak_tflops": FP32_PEAK_TFLOPS,
+        "kernel_ms_mean": kern_s * 1e3,
+        "algorithmic_bytes_per_launch": alg_bytes,
+        "flop_per_launch_direct_form": flops,
+    }
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -290,93 +320,109 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from dc_sand_b200 import DigitalDownConverter, _lib, taps
+    from dc_sand_b200 import DigitalDownConverter, _lib, cwg as dcwg, taps
+    from dc_sand_b200.scheduler import shard_range
+    from oracle import ddc_oracle as orc      # the checker of the parity spot checks below, never timed on this arm
 
-    packed = args.workload == "c3"
-    if packed:
-        n_streams, n = 64, 1 << 24
-    elif args.gpus == 1 and args.workload == "c2":
-        n_streams, n = 1, 1 << 28
-    else:
-        n_streams, n = 16, 1 << 24
-    if args.samples:
-        n = args.samples
-    if args.streams:
-        n_streams = args.streams
-
-    tmp = tempfile.mkdtemp()
-    ddc = DigitalDownConverter(D, FS, taps.write_csv("ddc_coeff_107MHz.csv", tmp), device=local)
-    m = ddc.out_len(n)
     lib = _lib.load()
-
-    # ---- inputs: pinned host buffers (e2e) and a device-resident copy (value) -----------------------------------
-    x_np = make_input(n_streams, n, rank, packed)
-    h_in = torch.from_numpy(x_np).pin_memory()
-    h_out = torch.empty((n_streams, m), dtype=torch.complex64).pin_memory()
-    d_in = h_in.to(dev, non_blocking=True)
-    d_out = torch.empty((n_streams, m), dtype=torch.complex64, device=dev)
-    torch.cuda.synchronize()
-    in_bytes = x_np.nbytes
-    out_bytes = n_streams * m * 8
-    del x_np
-
+    tmp = tempfile.mkdtemp()
+    csv107 = taps.write_csv("ddc_coeff_107MHz.csv", tmp)
+    hbm_peak, peak_src = measured_peaks()
     stream = torch.cuda.Stream(device=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
 
-    def device_pass(steps, per_launch_events):
-        evs = []
-        with torch.cuda.stream(stream):
-            for _ in range(steps):
-                if per_launch_events:
-                    e0 = torch.cuda.Event(enable_timing=True)
-                    e1 = torch.cuda.Event(enable_timing=True)
-                    e0.record(stream)
-                ddc.run_tensor(d_in, FC, out=d_out, packed=packed)
-                if per_launch_events:
-                    e1.record(stream)
-                    evs.append((e0, e1))
-        return evs
+    def gen_input(n_streams, n, packed, seed):
+        """Synthetic digitiser streams built in HBM (ddcb200_cwg, digitiser model of SURVEY 8d: tone + Gaussian noise, rounded
+        and clipped to 10 bits; Philox keyed by (seed, stream)), packed on the device when asked."""
+        x = dcwg.generate_carrier_wave_gpu(100.0, FC + 3.3e6, FS, n, 40.0, False, seed=seed, device=local, n_streams=n_streams,
+                                           digitise=True)
+        if packed:
+            xp = dcwg.pack10_gpu(x)
+            del x
+            return xp
+        return x
 
-    # warm-up
-    device_pass(max(args.warmup, 3), False)
-    torch.cuda.synchronize()
+    def time_device(ddc, d_in, d_out, packed, steps, warm, sampler=None):
+        """`steps` launches queued back to back on one stream between two CUDA events, behind a ~2 ms device-side delay so
+        that the host enqueues while the GPU waits (no launch latency inside the region).  Returns ms for all steps."""
+        with torch.cuda.stream(stream):
+            for _ in range(warm):
+                ddc.run_tensor(d_in, FC, out=d_out, packed=packed)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            torch.cuda._sleep(4_000_000)
+            e0.record(stream)
+            for _ in range(steps):
+                ddc.run_tensor(d_in, FC, out=d_out, packed=packed)
+            e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    def parity_window(ddc, d_in, d_out, packed, n, t, d, seed):
+        """max |y - oracle| / max|y| over one 512-output window of two streams (head window of stream 0, a random window of
+        another): the float64 windowed oracle on the samples read back from HBM.  Outside every timed region."""
+        rng = np.random.default_rng(seed)
+        m = d_out.shape[1]
+        step = orc.phase_step_cycles(n, FC, FS)
+        scale = float(d_out[:, : min(m, 1 << 16)].abs().max())
+        worst = 0.0
+        for s_i, m0 in ((0, 0), (int(rng.integers(0, d_in.shape[0])), int(rng.integers(0, max(m - 512, 1))) // 4 * 4)):
+            cnt = min(512, m - m0)
+            if packed:
+                seg = orc.unpack10(d_in[s_i, m0 * d // 4 * 5: ((m0 + cnt - 1) * d + t + 3) // 4 * 5].cpu().numpy()).astype(np.float32)
+            else:
+                seg = d_in[s_i, m0 * d: (m0 + cnt - 1) * d + t].cpu().numpy()
+            ref = orc.ddc_windowed_f64(seg, m0, cnt, step, ddc.ddc_filter_coeffs, d, x_base=m0 * d)
+            worst = max(worst, float(np.abs(d_out[s_i, m0:m0 + cnt].cpu().numpy() - ref).max()) / scale)
+        return worst
+
+    # ---- headline workload ---------------------------------------------------------------------------------------
+    packed = args.workload == "c3"
+    if packed:
+        n_streams, n = 64, 1 << 24
+    elif args.gpus == 1 and args.workload == "c2":
+        n_streams, n = 1, 1 << 28
+    else:
+        a, b = shard_range(TOTAL_STREAMS_C5, world, rank)     # strong scaling: the same 128 streams at every N
+        n_streams, n = b - a, 1 << 24
+    if args.samples:
+        n = args.samples
+    if args.streams:
+        n_streams = args.streams
+    total_streams = n_streams * world if (args.streams or packed or (args.gpus == 1 and args.workload == "c2")) else TOTAL_STREAMS_C5
+
+    ddc = DigitalDownConverter(D, FS, csv107, device=local)
+    m = ddc.out_len(n)
+    d_in = gen_input(n_streams, n, packed, seed=1234 + 4096 * rank)
+    d_out = torch.empty((n_streams, m), dtype=torch.complex64, device=dev)
+    in_bytes = d_in.numel() * d_in.element_size()
+    out_bytes = n_streams * m * 8
+
+    time_device(ddc, d_in, d_out, packed, 1, max(args.warmup, 3))
     barrier()
     launches0 = ddc.launch_count
-    # Timed region: K steps queued back to back on one stream between two CUDA events (an event pair around every launch
-    # would put two timestamp packets between consecutive kernels and measure those as well).
     with ClockSampler(local) as clk:
-        torch.cuda.synchronize()
-        t_start = torch.cuda.Event(enable_timing=True)
-        t_end = torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(stream):
-            # a ~2 ms device-side delay in front of the start event: the host enqueues the K launches while it runs, so the
-            # timed region holds K steps back to back and no host launch latency (about 0.1 ms before the first kernel)
-            torch.cuda._sleep(4_000_000)
-            t_start.record(stream)
-        device_pass(args.steps, False)
-        with torch.cuda.stream(stream):
-            t_end.record(stream)
-        torch.cuda.synchronize()
+        total_ms = time_device(ddc, d_in, d_out, packed, args.steps, 0)
     launches = ddc.launch_count - launches0
-    total_ms = t_start.elapsed_time(t_end)
-    barrier()
-    # diagnostic, outside the timed region: the same launches with an event pair around each one
-    evs = device_pass(min(args.steps, 20), True)
-    torch.cuda.synchronize()
-    kern_ms = [a.elapsed_time(b) for a, b in evs]
     variant = ddc.last_variant
+    barrier()
+    parity_err = parity_window(ddc, d_in, d_out, packed, n, T, D, seed=rank)
 
-    # ---- e2e: host buffers through the C ABI (H2D + kernel + D2H per step) ---------------------------------------
+    # ---- e2e: pinned host buffers through the C ABI (H2D + kernel + D2H per step) ---------------------------------
+    h_in = torch.empty(d_in.shape, dtype=d_in.dtype, pin_memory=True)
+    h_in.copy_(d_in)
+    h_out = torch.empty((n_streams, m), dtype=torch.complex64, pin_memory=True)
+    torch.cuda.synchronize()
     step = ddc.phase_step(n, FC)
     fn = lib.ddcb200_run_host_packed10 if packed else lib.ddcb200_run_host_f32
-    stride_in = h_in.stride(0)
     h = ddc._get_handle()
 
     def e2e_pass():
-        _lib.check(fn(h, h_in.data_ptr(), n, n_streams, stride_in, step, 0, h_out.data_ptr(), m), "run_host")
+        _lib.check(fn(h, h_in.data_ptr(), n, n_streams, h_in.stride(0), step, 0, h_out.data_ptr(), m), "run_host")
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     e2e_pass()
@@ -386,17 +432,17 @@ def run_ours(args):
         e2e_pass()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
-    # parity spot check of what the timed calls produced (device-resident result vs host-path result)
     # (tolerance, not bit equality: the host path runs time chunks, which may pair outputs differently in the fast FIR)
     a_dev, a_host = d_out[:, : min(m, 4096)].cpu(), h_out[:, : min(m, 4096)]
     same = bool((a_dev - a_host).abs().max() <= 1e-5 * a_dev.abs().max())
+    del h_in, h_out
 
     # ---- optional final gather of the outputs over NCCL (outside the timed region; the hot path has no collective) ---
     gather_ms = None
     if world > 1:
         from dc_sand_b200.scheduler import ShardedDDC
 
-        sh = ShardedDDC(world * n_streams, rank, world, ddc=ddc, center_freq=FC)
+        sh = ShardedDDC(TOTAL_STREAMS_C5 if not args.streams else world * n_streams, rank, world, ddc=ddc, center_freq=FC)
         torch.cuda.synchronize()
         dist.barrier()
         g0 = time.perf_counter()
@@ -404,28 +450,31 @@ def run_ours(args):
         torch.cuda.synchronize()
         gather_ms = (time.perf_counter() - g0) * 1e3
         if rank == 0:
-            assert full.shape == (world * n_streams, m)
+            assert full.shape == (sh.n_streams, m)
             assert torch.equal(full[:n_streams], d_out)
         del full
 
     # ---- max over ranks -------------------------------------------------------------------------------------------
     if os.environ.get("DDCB200_BENCH_VERBOSE"):
-        print(f"[rank {rank}] device {total_ms / args.steps:.4f} ms/step, e2e {e2e_s * 1e3:.2f} ms/step", file=sys.stderr, flush=True)
-    stats = torch.tensor([total_ms, e2e_s, float(np.median(kern_ms))], dtype=torch.float64, device=dev)
+        print(f"[rank {rank}] device {total_ms / args.steps:.4f} ms/step, e2e {e2e_s * 1e3:.2f} ms/step, parity {parity_err:.2e}",
+              file=sys.stderr, flush=True)
+    stats = torch.tensor([total_ms, e2e_s, parity_err], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    total_ms, e2e_s, kern_med_ms = [float(v) for v in stats.cpu()]
+    total_ms, e2e_s, parity_err = [float(v) for v in stats.cpu()]
+
+    extra = {}
+    if rank == 0 and world == 1 and args.workload == "c2" and not args.no_extra and not args.samples and not args.streams:
+        del d_in, d_out
+        torch.cuda.empty_cache()
+        extra = run_extras(args, torch, dev, local, gen_input, time_device, parity_window, hbm_peak, peak_src, csv107, tmp)
 
     if rank == 0:
-        samples_per_step = world * n_streams * n
+        samples_per_step = total_streams * n
         value = samples_per_step * args.steps / (total_ms * 1e-3) / 1e9
-        hbm_peak, peak_src = measured_peaks()
-        b_in = 1.25 if packed else 4.0
-        alg_bytes = n_streams * n * (b_in + 8.0 / D)            # per launch, per GPU
-        flops = 4.0 * T * m * n_streams                         # 2T real FMAs per output
         # average launch duration over the timed region (the region holds nothing but these launches, back to back)
         kern_s = total_ms * 1e-3 / max(int(launches), 1)
-        achieved = alg_bytes / kern_s / 1e9
+        wl = args.workload if (args.gpus == 1 or args.workload != "c2") else "c5"
         line = {
             "metric": "ddc_input_gsamples_per_s",
             "value": value,
@@ -435,12 +484,15 @@ def run_ours(args):
             "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps,
             "higher_is_better": True,
-            "scaling": "weak",
+            # configs[4] is a fixed job (128 streams) cut over N GPUs; its G = 1 point is extra.c5_g1 of the N = 1 line (the N = 1
+            # headline is configs[1], one 2^28-sample stream: the same samples per GPU as a rank of the N = 8 run)
+            "scaling": "strong",
             "vs_baseline": None,
             "dtype": "f32",
             "data": "synthetic",
             "config": {
                 "workload": workload_name(args),
+                "total_streams": total_streams,
                 "streams_per_gpu": n_streams,
                 "samples_per_stream": n,
                 "taps": T,
@@ -449,41 +501,151 @@ def run_ours(args):
                 "l2": f"input per launch {in_bytes / 2**20:.0f} MiB >> 126 MB L2 (no flush needed)",
                 "kernel": variant,
             },
-            "roofline": {
-                "bound": "hbm",
-                "achieved": achieved,
-                "peak": hbm_peak,
-                "unit": "GB/s",
-                "frac": achieved / hbm_peak,
-                "traffic": ncu_traffic(args.workload if (args.gpus == 1 or args.workload != "c2") else "c5", variant),
-                "peak_source": peak_src,
-                "frac_of_nominal_8TBs": achieved / 8000.0,
-                "fp32_tflops": flops / kern_s / 1e12,
-                "fp32_frac_of_74.4": flops / kern_s / 1e12 / FP32_PEAK_TFLOPS,
-                "kernel_ms_mean": kern_s * 1e3,
-                "kernel_ms_isolated_median": kern_med_ms,
-                "algorithmic_bytes_per_launch": alg_bytes,
-                "flop_per_launch": flops,
-            },
+            "roofline": roofline_of(n_streams, n, m, T, D, packed, kern_s, variant, hbm_peak, peak_src, ncu_traffic(wl, variant)),
             "e2e": {
-                "value": world * n_streams * n / e2e_s / 1e9,
+                "value": total_streams * n / e2e_s / 1e9,
                 "unit": "Gsamples/s",
                 "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": out_bytes,
                 "ms_per_step": e2e_s * 1e3,
                 "steps": e2e_steps,
+                "api": "ddcb200_run_host_* (C ABI, pinned host buffers, complex64 out)",
                 "matches_device_path": same,
             },
+            "parity_max_err": parity_err,
+            "parity_check": "max over ranks of |y - float64 windowed oracle| / max|y| on two 512-output windows per rank (tolerance 1e-5)",
             "gpu_launches": int(launches),
             "final_gather_ms_untimed": gather_ms,
             "numa_node_rank0": numa_node,
             "clocks": clk.summary(),
         }
+        if extra:
+            line["extra"] = extra
         if args.gpus == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_single_core()
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_extras(args, torch, dev, local, gen_input, time_device, parity_window, hbm_peak, peak_src, csv107, tmp):
+    """The other BASELINE configs on the same box, in the same run (one GPU): configs[2] (64 packed streams), configs[3] (the
+    25-cell tap / decimation sweep), configs[4] at G = 1 (the 128-stream workload on one GPU: the denominator of the strong-
+    scaling efficiency) and the drop-in DigitalDownConverter.run() on a pageable NumPy array."""
+    from scipy import signal
+
+    from dc_sand_b200 import DigitalDownConverter, _lib
+
+    lib = _lib.load()
+    extra = {}
+
+    # ---- configs[2]: 64 streams x 2^24 packed 10-bit samples ---------------------------------------------------------
+    s3, n3 = 64, 1 << 24
+    ddc = DigitalDownConverter(D, FS, csv107, device=local)
+    m3 = ddc.out_len(n3)
+    x3 = gen_input(s3, n3, True, seed=777)
+    y3 = torch.empty((s3, m3), dtype=torch.complex64, device=dev)
+    steps3 = 10
+    ms3 = time_device(ddc, x3, y3, True, steps3, 3) / steps3
+    v3 = ddc.last_variant
+    err3 = parity_window(ddc, x3, y3, True, n3, T, D, seed=3)
+    h_in = torch.empty(x3.shape, dtype=torch.uint8, pin_memory=True)
+    h_in.copy_(x3)
+    h_out = torch.empty((s3, m3), dtype=torch.complex64, pin_memory=True)
+    torch.cuda.synchronize()
+    step3 = ddc.phase_step(n3, FC)
+    hnd = ddc._get_handle()
+    e2e_t = []
+    for i in range(3):
+        t0 = time.perf_counter()
+        _lib.check(lib.ddcb200_run_host_packed10(hnd, h_in.data_ptr(), n3, s3, h_in.stride(0), step3, 0, h_out.data_ptr(), m3))
+        e2e_t.append(time.perf_counter() - t0)
+    e2e3 = min(e2e_t[1:])
+    extra["c3"] = {
+        "workload": "64 streams x 2^24 packed 10-bit samples, 256 taps, decimation 16 (BASELINE configs[2])",
+        "ms": ms3, "gsamples_per_s": s3 * n3 / ms3 / 1e6, "steps": steps3, "kernel": v3, "parity_max_err": err3,
+        "roofline": roofline_of(s3, n3, m3, T, D, True, ms3 * 1e-3, v3, hbm_peak, peak_src, ncu_traffic("c3", v3)),
+        "e2e": {"value": s3 * n3 / e2e3 / 1e9, "unit": "Gsamples/s", "ms_per_step": e2e3 * 1e3,
+                "h2d_bytes_per_step": x3.numel(), "d2h_bytes_per_step": s3 * m3 * 8},
+    }
+    del x3, y3, h_in, h_out
+    ddc.close()
+    torch.cuda.empty_cache()
+
+    # ---- configs[3]: taps 64 .. 1024 x decimation 4 .. 64, N = 2^26 float32 (256 MiB per launch > L2) ------------------
+    n4 = 1 << 26
+    x4 = gen_input(1, n4, False, seed=4242)
+    x4p = None
+    sweep, sweep_packed = [], []
+    for t in (64, 128, 256, 512, 1024):
+        for d in (4, 8, 16, 32, 64):
+            if t == 256:
+                csv = csv107
+            else:
+                csv = os.path.join(tmp, f"firwin_{t}_{d}.csv")
+                np.savetxt(csv, signal.firwin(t, 0.8 / d), fmt="%.18e")
+            c = DigitalDownConverter(d, FS, csv, device=local)
+            m4 = c.out_len(n4)
+            y4 = torch.empty((1, m4), dtype=torch.complex64, device=dev)
+            for pk, dst in ((False, sweep), (True, sweep_packed)):
+                if pk and x4p is None:
+                    from dc_sand_b200 import cwg as dcwg
+
+                    x4p = dcwg.pack10_gpu(x4)
+                xin = x4p if pk else x4
+                ms = time_device(c, xin, y4, pk, 10, 3) / 10
+                var = c.last_variant
+                r = roofline_of(1, n4, m4, t, d, pk, ms * 1e-3, var, hbm_peak, peak_src)
+                dst.append({"taps": t, "decimation": d, "ms": ms, "gsamples_per_s": n4 / ms / 1e6, "kernel": var.split("<")[0],
+                            "bound": r["bound"], "hbm_frac": r["frac"], "fp32_executed_frac": r["fp32_executed_frac"],
+                            "floor_frac": r["floor_frac"],
+                            "parity_max_err": parity_window(c, xin, y4, pk, n4, t, d, seed=t + d)})
+            del y4
+            c.close()
+    extra["sweep"] = {"workload": "1 stream x 2^26 float32 samples, firwin(T, 0.8 / D) taps (the shipped 107 MHz filter at T = 256); "
+                                  "3 warm-up + 10 launches per cell (BASELINE configs[3])", "cells": sweep}
+    extra["sweep_packed"] = {"workload": "the same cells on the packed 10-bit form of the same samples", "cells": sweep_packed}
+    del x4p
+    torch.cuda.empty_cache()
+
+    # ---- DigitalDownConverter.run(): the reference's own call, pageable float32 NumPy in, complex128 out (2^26 samples) ----
+    x_np = x4[0].cpu().numpy()
+    del x4
+    ddc = DigitalDownConverter(D, FS, csv107, device=local)
+    ddc.run(x_np[: 1 << 22], FC)
+    tr = []
+    for i in range(3):
+        t0 = time.perf_counter()
+        y = ddc.run(x_np, FC)
+        tr.append(time.perf_counter() - t0)
+    best = min(tr)
+    extra["e2e_run_api"] = {
+        "api": "DigitalDownConverter.run(np.ndarray float32 [2^26] pageable, 100e6) -> complex128 (feng/ddc/src/ddc.py:121)",
+        "value": n4 / best / 1e9, "unit": "Gsamples/s", "ms_per_call": best * 1e3, "calls": 3,
+        "h2d_bytes_per_step": x_np.nbytes, "d2h_bytes_per_step": int(y.shape[0]) * 8, "out_dtype": str(y.dtype),
+    }
+    del x_np, y
+    ddc.close()
+
+    # ---- configs[4] at G = 1: the 128-stream workload on ONE GPU (8 GiB in, 1 GiB out) -------------------------------------
+    s5, n5 = TOTAL_STREAMS_C5, 1 << 24
+    ddc = DigitalDownConverter(D, FS, csv107, device=local)
+    m5 = ddc.out_len(n5)
+    x5 = gen_input(s5, n5, False, seed=1234)
+    y5 = torch.empty((s5, m5), dtype=torch.complex64, device=dev)
+    steps5 = 5
+    ms5 = time_device(ddc, x5, y5, False, steps5, 3) / steps5
+    v5 = ddc.last_variant
+    extra["c5_g1"] = {
+        "workload": "128 streams x 2^24 float32 samples on ONE GPU (BASELINE configs[4] at G = 1: strong-scaling denominator)",
+        "ms": ms5, "gsamples_per_s": s5 * n5 / ms5 / 1e6, "steps": steps5, "kernel": v5,
+        "parity_max_err": parity_window(ddc, x5, y5, False, n5, T, D, seed=5),
+        "roofline": roofline_of(s5, n5, m5, T, D, False, ms5 * 1e-3, v5, hbm_peak, peak_src),
+    }
+    del x5, y5
+    ddc.close()
+    torch.cuda.empty_cache()
+    return extra
 
 
 def main():
@@ -497,6 +659,7 @@ def main():
     ap.add_argument("--streams", type=int, default=0, help="override streams per GPU")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="N = 1 only: skip the other BASELINE configs (extra.*)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

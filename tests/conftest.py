@@ -22,6 +22,17 @@ def meta():
 
 
 @pytest.fixture(scope="session")
+def meta_r2():
+    with open(os.path.join(GOLDEN, "meta_r2.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def golden_r2():
+    return np.load(os.path.join(GOLDEN, "ddc_r2.npz"))
+
+
+@pytest.fixture(scope="session")
 def golden_small():
     return np.load(os.path.join(GOLDEN, "ddc_small.npz"))
 

@@ -141,3 +141,13 @@ def test_pack10_roundtrip_all_codes_all_phases():
     rng = np.random.default_rng(0)
     s = rng.integers(-512, 512, size=4096).astype(np.int16)
     assert np.array_equal(orc.unpack10(orc.pack10(s)), s)
+
+
+def test_oracle_is_bit_identical_on_round2_reference_vectors(meta_r2, golden_r2):
+    """Input dtypes and argument corners beyond float32 (int16, int8, float64, complex input, negative centre frequency,
+    full-range uniform codes): vectors produced by the unmodified reference (tests/golden/make_golden_r2.py)."""
+    for name, m in meta_r2.items():
+        x = golden_r2[name + ":x"]
+        assert str(x.dtype) == m["in_dtype"]
+        y = orc.ddc_reference(x, m["fc"], _taps(m["csv"]), m["d"], m["fs"])
+        assert y.dtype == np.complex128 and np.array_equal(y, golden_r2[name + ":y"]), name
