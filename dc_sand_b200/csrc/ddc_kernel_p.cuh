@@ -66,262 +66,6 @@ struct PCfg {
     __host__ __device__ static constexpr int sub_base(int pr) { return (NPROD == 1 || pr == 0) ? 0 : (NSLOT + 1) / 2; }
 };
 
-template <int D, int JT, int KS, int MAXT>
-__global__ void __launch_bounds__(PCfg<D, JT, KS>::NWARPS * 32 + 32 * PCfg<D, JT, KS>::NPROD, 1)
-ddc_fused_p_kernel(const __grid_constant__ RunParams p, const __grid_constant__ TapsParam<MAXT> taps) {
-    using C = PCfg<D, JT, KS>;
-    constexpr int ROW = C::ROW, R = C::R, NW = C::NW, SRP = C::SRP, NWARPS = C::NWARPS, NG = C::NGROUPS;
-    constexpr int RO = C::RO, NSLOT = C::NSLOT;
-    constexpr int WANT = C::TOT_ROWS * ROW;   // samples staged per chunk
-
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);          // [16]
-    uint64_t* empty_bar = full_bar + 16;                                 // [16]
-    float2* slot_rot = reinterpret_cast<float2*>(smem_raw + 256);        // [16] NCO rotation of the chunk in each slot
-    volatile int* slot_seq = reinterpret_cast<volatile int*>(smem_raw + 384);   // [16] chunk currently staged in each slot
-    float* buf = reinterpret_cast<float*>(smem_raw + C::HDR_BYTES);
-
-    const int tid = threadIdx.x;
-    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform (keeps loop state in uniform registers)
-    const int lane = tid & 31;
-
-    if (tid == 0) {
-#pragma unroll 1
-        for (int s = 0; s < NSLOT; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], KS);
-            slot_seq[s] = -1;
-        }
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    // chunk k of this CTA is global chunk blockIdx.x + k * gridDim.x (stream-major numbering); it is computed by warp
-    // group k % NG in slot k % NSLOT.  (stream, chunk-in-stream) advance incrementally.
-    const int cps = (int)p.tiles_per_stream;                 // chunks per stream
-    const int n_k = (int)((p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
-    const unsigned long long chunk_dph = (unsigned long long)((long long)C::CHUNK_OUT * D) * p.step_fx;
-
-    if (warp >= NWARPS) {
-        // ------------------------------------------------------------------ producer warps
-        // One producer cannot keep up (each bulk copy costs it tens of issue cycles next to FFMA2-saturated warps), so
-        // chunk k is staged by producer k % NPROD.
-        constexpr int NP = C::NPROD;
-        const int pid = warp - NWARPS;
-        const long long pstride = (long long)NP * gridDim.x;
-        const int gs = (int)(pstride / cps), gc = (int)(pstride % cps);
-        const long long pfirst = blockIdx.x + (long long)pid * gridDim.x;
-        int cs = (int)(pfirst / cps), cc = (int)(pfirst % cps);
-        // Each producer owns its own sub-ring of slots (and serves the warp groups of the same parity): with a shared
-        // ring one producer could lap the other by a whole pass, which a parity wait cannot detect.
-        const int sbase = C::sub_base(pid), scnt = C::sub_count(pid);
-        int sidx = 0;
-        uint32_t par = 1;  // first pass over the ring: slots are free
-        for (int k = pid; k < n_k && (p.debug_mode & 255) != 1; k += NP) {
-            const int slot = sbase + sidx;
-            if (p.debug_mode & 256) __nanosleep(300);
-            if (lane == 0) {
-                mbar_wait(&empty_bar[slot], par);   // one waiter: the other lanes only help with ragged chunks
-                // Publish which chunk this slot now holds.  Successive uses of a slot are consumed by DIFFERENT warp groups,
-                // so a group may reach its wait before the slot's previous use has even landed; a parity wait cannot tell
-                // "two phases early" from "done".  Consumers therefore first wait for slot_seq == their chunk.
-                slot_seq[slot] = k;
-            }
-            __syncwarp();
-            const float* src = reinterpret_cast<const float*>(p.in) + (long long)cs * p.in_stride + (long long)cc * C::CHUNK_S;
-            float* dst = buf + (size_t)slot * C::SLOT_FLOATS;
-            const long long valid = p.n_samples - (long long)cc * C::CHUNK_S;
-#if DDCB200_PROD_ROT
-            if (lane == 0) slot_rot[slot] = nco_rot(p.phase0_fx + (unsigned long long)cc * chunk_dph);
-#endif
-            if (valid >= WANT) {
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)WANT * 4u);   // release: slot_rot becomes visible
-#pragma unroll
-                    for (int sr = 0; sr < C::NSR; ++sr) {
-                        constexpr int SR4 = C::SROWS;
-                        const int nrow = (C::TOT_ROWS - sr * SR4) < SR4 ? (C::TOT_ROWS - sr * SR4) : SR4;
-                        bulk_g2s(dst + sr * SRP, src + sr * SR4 * ROW, (uint32_t)nrow * ROW * 4u, &full_bar[slot]);
-                    }
-                }
-            } else {
-                // ragged last chunk of a stream: whole 16-byte groups by TMA, the last 1-3 samples by hand, zeros after
-                uint32_t tx = 0;
-                for (int sr = 0; sr < C::NSR; ++sr) {
-                    const int cap = ((C::TOT_ROWS - sr * C::SROWS) < C::SROWS ? (C::TOT_ROWS - sr * C::SROWS) : C::SROWS) * ROW;
-                    const long long s0 = (long long)sr * C::SROWS * ROW;
-                    long long cnt = valid - s0;
-                    cnt = cnt < 0 ? 0 : (cnt > cap ? cap : cnt);
-                    const int bulk = (int)cnt & ~3;
-                    for (int e = bulk + lane; e < cap; e += 32) dst[sr * SRP + e] = (e < (int)cnt) ? src[s0 + e] : 0.f;
-                    tx += (uint32_t)bulk * 4u;
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&full_bar[slot], tx);
-                    for (int sr = 0; sr < C::NSR; ++sr) {
-                        const int cap = ((C::TOT_ROWS - sr * C::SROWS) < C::SROWS ? (C::TOT_ROWS - sr * C::SROWS) : C::SROWS) * ROW;
-                        const long long s0 = (long long)sr * C::SROWS * ROW;
-                        long long cnt = valid - s0;
-                        cnt = cnt < 0 ? 0 : (cnt > cap ? cap : cnt);
-                        const int bulk = (int)cnt & ~3;
-                        if (bulk > 0) bulk_g2s(dst + sr * SRP, src + s0, (uint32_t)bulk * 4u, &full_bar[slot]);
-                    }
-                }
-            }
-            __syncwarp();
-            if (++sidx == scnt) { sidx = 0; par ^= 1u; }
-            cs += gs;
-            cc += gc;
-            if (cc >= cps) { cc -= cps; ++cs; }
-            // pull the chunk this CTA will stage `l2_ahead` iterations from now into L2, so that the ring only has to
-            // cover the L2 -> shared-memory latency, not the HBM latency
-            if (lane == 0 && p.l2_ahead > 0 && k + p.l2_ahead < n_k) {
-                const long long gk = blockIdx.x + (long long)(k + p.l2_ahead) * gridDim.x;
-                const long long ps = gk / cps, pc = gk - ps * cps;
-                const long long pvalid = p.n_samples - pc * C::CHUNK_S;
-                const long long nb = (pvalid < C::CHUNK_S ? pvalid : C::CHUNK_S) * 4;
-                if (nb >= 16) {
-                    const float* pf = reinterpret_cast<const float*>(p.in) + ps * p.in_stride + pc * C::CHUNK_S;
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf), "r"((uint32_t)(nb & ~15LL)) : "memory");
-                }
-            }
-        }
-    } else {
-        // ------------------------------------------------------------------ compute warps
-        const int grp = warp % NG;                            // chunk group (warps grp and grp + NG share a chunk)
-        const int part = warp / NG;                           // which phase groups / outputs are mine (warp-uniform)
-        const int g = (lane & 7) * C::SROWS + (lane >> 3);    // thread-row within the chunk
-        int rowoff[C::HALO_ROWS + 1];
-#pragma unroll
-        for (int h = 0; h <= C::HALO_ROWS; ++h) rowoff[h] = C::row_offset(g + h);
-        const int rbeg = (R >= KS) ? part * RO : 0;           // first output of the thread-row this thread finishes
-        // NCO: output m = chunk*CHUNK_OUT + g*R + r is rotated by rot_chunk * rot_thr[r]
-        float2 rot_thr[RO];
-#pragma unroll
-        for (int r = 0; r < RO; ++r) rot_thr[r] = nco_rot((unsigned long long)((long long)(g * R + rbeg + r) * D) * p.step_fx);
-
-        const long long kstride = (long long)NG * gridDim.x;
-        const int gs = (int)(kstride / cps), gc = (int)(kstride % cps);
-        const long long first = blockIdx.x + (long long)grp * gridDim.x;
-        int cs = (int)(first / cps), cc = (int)(first % cps);
-        // chunk k = grp + NG*i is the (grp/NP + (NG/NP)*i)-th chunk of producer grp % NP
-        const int sbase = C::sub_base(grp % C::NPROD), scnt = C::sub_count(grp % C::NPROD);
-        int sidx = (grp / C::NPROD) % scnt;
-        uint32_t par = (uint32_t)((grp / C::NPROD) / scnt) & 1u;
-        for (int k = grp; k < n_k; k += NG) {
-            const int slot = sbase + sidx;
-            if ((p.debug_mode & 255) != 1) {
-                while (slot_seq[slot] != k) {}      // the producer has re-armed this slot for MY chunk (see producer)
-                mbar_wait(&full_bar[slot], par);
-            }
-            float* sbuf = buf + (size_t)slot * C::SLOT_FLOATS;
-#if DDCB200_PROD_ROT
-            const float2 rot_chunk = ((p.debug_mode & 255) != 1) ? slot_rot[slot] : make_float2(1.f, 0.f);
-#else
-            const float2 rot_chunk = nco_rot(p.phase0_fx + (unsigned long long)cc * chunk_dph);
-#endif
-
-            float2 acc[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
-
-            const int npg = ((p.debug_mode & 255) == 2) ? 0 : C::VPW;
-            // two separate induction variables: `xoff` (per-thread shared-memory offset, hidden from the induction-
-            // variable optimiser) and `tp` (uniform tap pointer); if they shared the counter pg the compiler would keep
-            // it in a vector register and fetch taps with per-thread LDC instead of LDCU -> uniform-register operands
-            int xoff = part * C::VPW * 4;
-            const float4* tp = &taps.c2[part * C::VPW * 2];   // taps (j*D + 4*pg + {0,1}) and (+{2,3}) as two float4
-#pragma unroll 1
-            for (int pg = 0; pg < npg; ++pg, tp += 2) {
-                asm volatile("" : "+r"(xoff));
-                float4 w[NW];
-#pragma unroll
-                for (int b = 0; b < NW; ++b)
-                    w[b] = *reinterpret_cast<const float4*>(sbuf + xoff + rowoff[b / R] + (b % R) * D);
-                xoff += 4;
-#pragma unroll
-                for (int j = 0; j < JT; ++j) {
-                    const float4 ta = tp[j * (D / 2)], tb = tp[j * (D / 2) + 1];
-#pragma unroll
-                    for (int r = 0; r < R; ++r) acc[r] = ffma2(w[r + j].x, make_float2(ta.x, ta.y), acc[r]);
-#pragma unroll
-                    for (int r = 0; r < R; ++r) acc[r] = ffma2(w[r + j].y, make_float2(ta.z, ta.w), acc[r]);
-#pragma unroll
-                    for (int r = 0; r < R; ++r) acc[r] = ffma2(w[r + j].z, make_float2(tb.x, tb.y), acc[r]);
-#pragma unroll
-                    for (int r = 0; r < R; ++r) acc[r] = ffma2(w[r + j].w, make_float2(tb.z, tb.w), acc[r]);
-                }
-            }
-
-            float2 y[RO];
-            bool writer = true;
-            if (KS == 1) {
-                __syncwarp();
-                if (lane == 0 && (p.debug_mode & 255) != 1) mbar_arrive(&empty_bar[slot]);   // slot back to the producer
-#pragma unroll
-                for (int r = 0; r < RO; ++r) y[r] = acc[r];
-            } else {
-                // my shared-memory reads of the chunk are done
-                __syncwarp();
-                if (lane == 0 && (p.debug_mode & 255) != 1) mbar_arrive(&empty_bar[slot]);   // both warps arrive: slot is free
-                // exchange partial sums with the partner warp: I send the partials of the outputs my partner finishes.
-                // First barrier: the partner has read what I sent for the previous chunk; second: it has written.
-                const int bar_id = 1 + grp;
-                float2* xb = reinterpret_cast<float2*>(smem_raw + 512) + (size_t)grp * 2 * 32 * RO;
-                float2* xs = xb + (part * 32 + lane) * RO;
-                const float2* xr = xb + ((part ^ 1) * 32 + lane) * RO;
-                asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-                if (R >= KS) {
-#pragma unroll
-                    for (int r = 0; r < RO; ++r) xs[r] = acc[(part ^ 1) * RO + r];
-                } else {
-                    if (part) xs[0] = acc[0];
-                }
-                asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-                if (R >= KS) {
-#pragma unroll
-                    for (int r = 0; r < RO; ++r) {
-                        const float2 v = xr[r];
-                        y[r] = make_float2(acc[part * RO + r].x + v.x, acc[part * RO + r].y + v.y);
-                    }
-                } else {
-                    const float2 v = part ? make_float2(0.f, 0.f) : xr[0];
-                    y[0] = make_float2(acc[0].x + v.x, acc[0].y + v.y);
-                    writer = (part == 0);
-                }
-            }
-
-            // epilogue: NCO rotation and store of this thread's RO consecutive outputs
-            const long long m0 = (long long)cc * C::CHUNK_OUT + g * R + rbeg;
-            float2* o = p.out + (long long)cs * p.out_stride + m0;
-#pragma unroll
-            for (int r = 0; r < RO; ++r) y[r] = cmul(cmul(y[r], rot_thr[r]), rot_chunk);
-            if (writer && !(p.debug_mode & 512)) {
-                if (m0 + RO <= p.n_out) {
-                    if (p.vec_store && (RO % 2 == 0)) {
-#pragma unroll
-                        for (int r = 0; r < RO; r += 2)
-                            __stcs(reinterpret_cast<float4*>(o + r), make_float4(y[r].x, y[r].y, y[r + 1].x, y[r + 1].y));
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < RO; ++r) __stcs(o + r, y[r]);
-                    }
-                } else {
-#pragma unroll
-                    for (int r = 0; r < RO; ++r)
-                        if (m0 + r < p.n_out) __stcs(o + r, y[r]);
-                }
-            }
-            sidx += NG / C::NPROD;
-            if (sidx >= scnt) { sidx -= scnt; par ^= 1u; }
-            cs += gs;
-            cc += gc;
-            if (cc >= cps) { cc -= cps; ++cs; }
-        }
-    }
-}
-
 // =============================================================================================================
 // Default float32 variant: same ring and FIR as ddc_fused_p_kernel<KS = 1>, but the epilogue of chunk i (NCO rotation,
 // address arithmetic, stores: ~160 mostly dependent instructions) is DEFERRED into the first phase-group pass of chunk

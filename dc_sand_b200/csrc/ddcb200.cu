@@ -1,9 +1,6 @@
 // C-ABI implementation of include/ddcb200.h: handle management, per-call host-side preparation of the folded
-// complex taps (float64 -> float32), kernel dispatch, and the chunked double-buffered host path.
-#include "../../include/ddcb200.h"
-
-#include <cuda_runtime.h>
-
+// complex taps (float64 -> float32), kernel dispatch, and the chunked double-buffered host path.  The fused kernels are
+// launched through ddch::launch_* (one translation unit per kernel family, k_*.cu).
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -15,14 +12,12 @@
 #include <thread>
 #include <vector>
 
+#include "ddc_host.h"
 #include "ddc_kernels.cuh"
-#include "ddc_kernel_p.cuh"
-#include "ddc_kernel_w.cuh"
-#include "ddc_kernel_ws.cuh"
 
 using namespace ddck;
 
-namespace {
+namespace ddch {
 
 thread_local char g_err[512] = "";
 
@@ -34,15 +29,11 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
-#define CUDA_TRY(expr)                                                                                      \
-    do {                                                                                                    \
-        cudaError_t e_ = (expr);                                                                            \
-        if (e_ != cudaSuccess) return fail(DDCB200_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    } while (0)
+}  // namespace ddch
 
-constexpr int kStages = 3;     // TMA pipeline depth
-constexpr int kS = 32;         // thread-rows per TMA bulk copy (super-row)
-constexpr int kMaxTapsFused = 2048;
+using ddch::fail;
+
+namespace {
 
 struct DeviceGuard {
     int prev = -1;
@@ -73,56 +64,6 @@ cudaError_t copy_rows_async(void* dst, size_t dpitch, const void* src, size_t sp
 
 }  // namespace
 
-struct ddcb200 {
-    int device = 0;
-    int sm_count = 0;
-    int decim = 1;
-    std::vector<double> taps;       // raw, file order
-    double taps_sum = 0.0;
-    cudaStream_t stream = nullptr;  // compute
-    cudaStream_t copy_in = nullptr, copy_out = nullptr;
-    // device scratch for the generic/short kernels' taps (ring so that back-to-back calls do not race)
-    static constexpr int kRing = 8;
-    float2* d_ctaps[kRing] = {};
-    float2* h_ctaps[kRing] = {};    // pinned
-    cudaEvent_t ring_ev[kRing] = {};
-    int ring_cap = 0, ring_pos = 0;
-    // host-path workspace
-    static constexpr int kBufs = 3;
-    void* d_chunk_in[kBufs] = {};
-    ddcb200_c64* d_chunk_out[kBufs] = {};
-    size_t chunk_in_cap = 0, chunk_out_cap = 0;
-    cudaEvent_t ev_in[kBufs] = {}, ev_k[kBufs] = {}, ev_out[kBufs] = {};
-    int64_t chunk_samples = 1 << 24;
-    int64_t launches = 0;
-    int force_variant = 0;
-    int debug_mode = 0;
-    int stagger_cycles = 0;
-    int l2_ahead = 0;
-    unsigned long long* d_dbg = nullptr;   // diagnostic counters (option "dbg_counters")
-    std::string last_variant = "none";
-    bool smem_attr_set = false;
-    // folded fast-FIR taps of the last (step, jt, D): streaming callers repeat the same step call after call
-    std::vector<float2> wt_cache;
-    double wt_step = 0.0;
-    int wt_jt = 0, wt_d = 0, wt_nest = 0;
-    // pinned staging for pageable host input (see staged_h2d)
-    static constexpr int kStage = 2;
-    static constexpr size_t kStageBytes = 8u << 20;
-    void* h_stage[kStage] = {};
-    cudaEvent_t ev_stage[kStage] = {};
-    int stage_pos = 0;
-    int copy_threads = 4;
-    float* d_unpack_ws = nullptr;          // float32 workspace of the two-launch packed path (unpack, then a float32 kernel)
-    size_t unpack_ws_cap = 0;
-    cudaEvent_t unpack_ev = nullptr;       // end of the last kernel that read the workspace (calls may come on different streams)
-    ddcb200_c64* h_ostage[kBufs] = {};   // pinned landing buffers for the complex128 host path (one per chunk buffer)
-    size_t ostage_cap = 0;
-    std::vector<float2> wq_cache;   // same for the small-decimation kernel
-    double wq_step = 0.0;
-    int wq_jt = 0, wq_nq = 0;
-};
-
 namespace {
 
 // Host-path calls queue work on three streams and read / write the caller's host buffers asynchronously: whatever way such a
@@ -138,6 +79,9 @@ struct DrainGuard {
     }
 };
 
+}  // namespace
+
+namespace ddch {
 // c[k] = taps[T-1-k]/sum * exp(-j 2 pi k step), float64 -> float32; zero padded to n_pad
 void make_ctaps(const ddcb200* h, double step, int n_pad, float2* out) {
     const int T = (int)h->taps.size();
@@ -157,6 +101,7 @@ void make_ctaps(const ddcb200* h, double step, int n_pad, float2* out) {
 
 // Kernel W (fast FIR, ddc_kernel_w.cuh): for tap pair i and phase d the three tap sets
 //   seq 0: c[2i D + d],  seq 1: c[2i D + d] + c[(2i+1) D + d],  seq 2: c[(2i+1) D + d]      at index (3i + seq) D + d,
+namespace {
 // formed in float64 from the folded taps and rounded to float32 once.
 void make_wtaps(const ddcb200* h, double step, int jt, int D, float2* out) {
     const int T = (int)h->taps.size();
@@ -182,72 +127,11 @@ void make_wtaps(const ddcb200* h, double step, int jt, int D, float2* out) {
 }
 
 // Kernel WQ (small decimations, ddc_kernel_w.cuh): NQ = 16 / D shifted tap sets c_q[k'] = c[k' - D q] (same phase law in k'),
-// each laid out like kernel W's: index q * 3 (jt/2) 16 + (3 i + seq) 16 + d.
-void make_wqtaps(const ddcb200* h, double step, int jt, int nq, int D, float2* out) {
-    const int T = (int)h->taps.size();
-    const double fstep = step - std::floor(step);
-    for (int q = 0; q < nq; ++q) {
-        auto c = [&](int kp, double& re, double& im) {
-            const int k = kp - D * q;
-            if (k < 0 || k >= T) { re = im = 0.0; return; }
-            const double hk = h->taps[T - 1 - k] / h->taps_sum;
-            double ph = fstep * (double)kp;
-            ph -= std::floor(ph);
-            const double a = -2.0 * M_PI * ph;
-            re = hk * std::cos(a);
-            im = hk * std::sin(a);
-        };
-        float2* o = out + (size_t)q * 3 * (jt / 2) * 16;
-        for (int i = 0; i < jt / 2; ++i)
-            for (int d = 0; d < 16; ++d) {
-                double er, ei, orr, oi;
-                c(2 * i * 16 + d, er, ei);
-                c((2 * i + 1) * 16 + d, orr, oi);
-                o[(3 * i + 0) * 16 + d] = make_float2((float)er, (float)ei);
-                o[(3 * i + 1) * 16 + d] = make_float2((float)(er + orr), (float)(ei + oi));
-                o[(3 * i + 2) * 16 + d] = make_float2((float)orr, (float)oi);
-            }
-    }
-}
-
-// Nested fast FIR (w2_fir_pg): for tap quad iota and phase d the nine tap sets (a, b) at index ((9 iota + 3 a + b) D + d):
-//   g_0[i] = c[2i], g_1[i] = c[2i] + c[2i+1], g_2[i] = c[2i+1];   h_a0 = g_a[2 iota], h_a1 = g_a[2 iota] + g_a[2 iota + 1], h_a2 = g_a[2 iota + 1]
-void make_w2taps(const ddcb200* h, double step, int jt, int D, float2* out) {
-    const int T = (int)h->taps.size();
-    const double fstep = step - std::floor(step);
-    auto c = [&](int k, double* v) {
-        v[0] = v[1] = 0.0;
-        if (k >= T) return;
-        const double hk = h->taps[T - 1 - k] / h->taps_sum;
-        double ph = fstep * (double)k;
-        ph -= std::floor(ph);
-        const double a = -2.0 * M_PI * ph;
-        v[0] = hk * std::cos(a);
-        v[1] = hk * std::sin(a);
-    };
-    for (int io = 0; io < jt / 4; ++io)
-        for (int d = 0; d < D; ++d) {
-            double cb[4][2], g[3][2][2];   // c of blocks 4 io .. 4 io + 3; g[a][i - 2 io]
-            for (int b = 0; b < 4; ++b) c((4 * io + b) * D + d, cb[b]);
-            for (int i = 0; i < 2; ++i)
-                for (int z = 0; z < 2; ++z) {
-                    g[0][i][z] = cb[2 * i][z];
-                    g[1][i][z] = cb[2 * i][z] + cb[2 * i + 1][z];
-                    g[2][i][z] = cb[2 * i + 1][z];
-                }
-            for (int a = 0; a < 3; ++a) {
-                float2* o = out + (size_t)(9 * io + 3 * a) * D + d;
-                o[0] = make_float2((float)g[a][0][0], (float)g[a][0][1]);
-                o[D] = make_float2((float)(g[a][0][0] + g[a][1][0]), (float)(g[a][0][1] + g[a][1][1]));
-                o[2 * D] = make_float2((float)g[a][1][0], (float)g[a][1][1]);
-            }
-        }
-}
+}  // namespace
 
 // cached front end of make_wtaps (invalidated by set_taps / set_decimation through wt_jt = 0)
 const float2* cached_wtaps(ddcb200* h, double step, int jt, int D) {
-    if (h->wt_jt != jt || h->wt_d != D || h->wt_nest != 0 || h->wt_step != step || h->wt_cache.size() != (size_t)(3 * (jt / 2) * D)) {
-        h->wt_nest = 0;
+    if (h->wt_jt != jt || h->wt_d != D || h->wt_step != step || h->wt_cache.size() != (size_t)(3 * (jt / 2) * D)) {
         h->wt_cache.resize((size_t)(3 * (jt / 2) * D));
         make_wtaps(h, step, jt, D, h->wt_cache.data());
         h->wt_step = step;
@@ -255,334 +139,6 @@ const float2* cached_wtaps(ddcb200* h, double step, int jt, int D) {
         h->wt_d = D;
     }
     return h->wt_cache.data();
-}
-
-unsigned long long to_fx64(double frac01) {
-    // frac01 in [0,1) -> round(frac * 2^64) mod 2^64 using long double (64-bit mantissa on x86)
-    long double v = (long double)frac01 * 18446744073709551616.0L;
-    if (v >= 18446744073709551615.0L) return 0ull;
-    return (unsigned long long)(v + 0.5L);
-}
-
-unsigned long long phase_of(double step, int64_t sample_offset) {
-    // frac(sample_offset * step) * 2^64, exact modular arithmetic on the fixed-point step
-    const double fstep = step - std::floor(step);
-    const unsigned long long sfx = to_fx64(fstep);
-    return (unsigned long long)sample_offset * sfx;
-}
-
-int ensure_ring(ddcb200* h, int n_taps) {
-    if (n_taps <= h->ring_cap) return DDCB200_OK;
-    const int cap = std::max(n_taps, 1024);
-    for (int i = 0; i < ddcb200::kRing; ++i) {
-        if (h->d_ctaps[i]) cudaFree(h->d_ctaps[i]);
-        if (h->h_ctaps[i]) cudaFreeHost(h->h_ctaps[i]);
-        h->d_ctaps[i] = nullptr;
-        h->h_ctaps[i] = nullptr;
-        CUDA_TRY(cudaMalloc(&h->d_ctaps[i], sizeof(float2) * cap));
-        CUDA_TRY(cudaMallocHost(&h->h_ctaps[i], sizeof(float2) * cap));
-        if (!h->ring_ev[i]) CUDA_TRY(cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming));
-    }
-    h->ring_cap = cap;
-    return DDCB200_OK;
-}
-
-static inline bool aligned_f32(const void* d_in, int64_t in_stride, bool packed) {
-    return !packed && (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (in_stride % 4 == 0);
-}
-
-template <int D, int R, int KS, int MAXT>
-int launch_fused(ddcb200* h, RunParams& p, const float2* ctaps_host, cudaStream_t st, int grid_limit) {
-    using C = FusedCfg<D, R, kS, KS>;
-    auto kern = ddc_fused_kernel<D, R, kS, KS, kStages, MAXT, false>;
-    const size_t smem = 128 + C::XBUF_BYTES + (size_t)kStages * C::stage_floats(p.halo_rows) * sizeof(float);
-    if (smem > 227 * 1024) return fail(DDCB200_EINVAL, "fused kernel needs %zu bytes of shared memory", smem);
-    static size_t smem_set[64] = {};  // per device
-    if (h->device < 64 && smem_set[h->device] < smem) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set[h->device] = smem;
-    }
-    TapsParam<MAXT> tp;
-    std::memset(&tp, 0, sizeof(tp));
-    std::memcpy(tp.c2, ctaps_host, sizeof(float2) * (size_t)p.n_taps);
-    const long long grid = std::min<long long>(p.total_tiles, grid_limit);
-    kern<<<(unsigned)grid, C::NT + 32, smem, st>>>(p, tp);
-    CUDA_TRY(cudaGetLastError());
-    h->launches++;
-    char name[96];
-    snprintf(name, sizeof(name), "fused_tma<D%d,R%d,S%d,KS%d,STAGES%d,MAXT%d>", D, R, kS, KS, kStages, MAXT);
-    h->last_variant = name;
-    return DDCB200_OK;
-}
-
-template <int D, int R>
-int launch_fused_t(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, int grid_limit, int ks) {
-    if constexpr (R <= 4) {  // larger R: exchange buffer / register budget do not fit 544 threads
-        if (ks == 2) {
-            if (p.n_taps <= 512) return launch_fused<D, R, 2, 512>(h, p, ct, st, grid_limit);
-            return launch_fused<D, R, 2, kMaxTapsFused>(h, p, ct, st, grid_limit);
-        }
-    }
-    if (p.n_taps <= 512) return launch_fused<D, R, 1, 512>(h, p, ct, st, grid_limit);
-    return launch_fused<D, R, 1, kMaxTapsFused>(h, p, ct, st, grid_limit);
-}
-
-template <int D, int JT, int KS>
-int launch_p(ddcb200* h, RunParams& p, const float2* ctaps_host, cudaStream_t st) {
-    using C = PCfg<D, JT, KS>;
-    constexpr int MAXT = JT * D;
-    auto kern = ddc_fused_p_kernel<D, JT, KS, MAXT>;
-    const size_t smem = C::HDR_BYTES + (size_t)C::NSLOT * C::SLOT_FLOATS * sizeof(float);
-    static bool attr_set[64] = {};
-    if (h->device < 64 && !attr_set[h->device]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[h->device] = true;
-    }
-    TapsParam<MAXT> tp;
-    std::memset(&tp, 0, sizeof(tp));
-    std::memcpy(tp.c2, ctaps_host, sizeof(float2) * (size_t)std::min(p.n_taps, MAXT));
-    const long long grid = std::min<long long>(p.total_tiles, h->sm_count);
-    kern<<<(unsigned)grid, C::NWARPS * 32 + 32 * C::NPROD, smem, st>>>(p, tp);
-    CUDA_TRY(cudaGetLastError());
-    h->launches++;
-    char name[96];
-    snprintf(name, sizeof(name), "fused_phase_major<D%d,R%d,J%d,KS%d,SLOTS%d>", D, C::R, JT, KS, C::NSLOT);
-    h->last_variant = name;
-    return DDCB200_OK;
-}
-
-template <int D, int JT>
-int launch_p10(ddcb200* h, RunParams& p, const float2* ctaps_host, cudaStream_t st) {
-    using C = P10Cfg<D, JT>;
-    constexpr int MAXT = JT * D;
-    auto kern = ddc_fused_p10_kernel<D, JT, MAXT>;
-    const size_t smem = 512 + (size_t)C::FLOAT_BYTES + (size_t)C::NRAW * C::RAW_BYTES;
-    static bool attr_set[64] = {};
-    if (h->device < 64 && !attr_set[h->device]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[h->device] = true;
-    }
-    TapsParam<MAXT> tp;
-    std::memset(&tp, 0, sizeof(tp));
-    std::memcpy(tp.c2, ctaps_host, sizeof(float2) * (size_t)std::min(p.n_taps, MAXT));
-    const long long grid = std::min<long long>(p.total_tiles, h->sm_count);
-    kern<<<(unsigned)grid, C::NWARPS * 32 + 32 * C::NPROD, smem, st>>>(p, tp);
-    CUDA_TRY(cudaGetLastError());
-    h->launches++;
-    char name[96];
-    snprintf(name, sizeof(name), "fused_phase_major_packed10<D%d,R%d,J%d,RAWSLOTS%d>", D, C::R, JT, C::NRAW);
-    h->last_variant = name;
-    return DDCB200_OK;
-}
-
-template <int D>
-int launch_p10_j(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, int jt) {
-    switch (jt) {
-        case 4: return launch_p10<D, 4>(h, p, ct, st);
-        case 8: return launch_p10<D, 8>(h, p, ct, st);
-        default: return launch_p10<D, 16>(h, p, ct, st);
-    }
-}
-
-template <int D, int JT>
-int launch_pd(ddcb200* h, RunParams& p, const float2* ctaps_host, cudaStream_t st) {
-    using C = PCfg<D, JT, 1>;
-    constexpr int MAXT = JT * D;
-    auto kern = ddc_fused_pd_kernel<D, JT, MAXT>;
-    const size_t smem = C::HDR_BYTES + (size_t)C::NSLOT * C::SLOT_FLOATS * sizeof(float);
-    static bool attr_set[64] = {};
-    if (h->device < 64 && !attr_set[h->device]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[h->device] = true;
-    }
-    TapsParam<MAXT> tp;
-    std::memset(&tp, 0, sizeof(tp));
-    std::memcpy(tp.c2, ctaps_host, sizeof(float2) * (size_t)std::min(p.n_taps, MAXT));
-    const long long grid = std::min<long long>(p.total_tiles, h->sm_count);
-    kern<<<(unsigned)grid, C::NWARPS * 32 + 32 * C::NPROD, smem, st>>>(p, tp);
-    CUDA_TRY(cudaGetLastError());
-    h->launches++;
-    char name[96];
-    snprintf(name, sizeof(name), "fused_phase_major_deferred<D%d,R%d,J%d,SLOTS%d>", D, C::R, JT, C::NSLOT);
-    h->last_variant = name;
-    return DDCB200_OK;
-}
-
-template <int D>
-int launch_pd_j(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, int jt) {
-    switch (jt) {
-        case 4: return launch_pd<D, 4>(h, p, ct, st);
-        case 8: return launch_pd<D, 8>(h, p, ct, st);
-        default: return launch_pd<D, 16>(h, p, ct, st);
-    }
-}
-
-template <int D, int JT, int NEST>
-int launch_w(ddcb200* h, RunParams& p, cudaStream_t st, double step) {
-    using C = WCfg<D, JT>;
-    constexpr int NT = NEST ? C::NTW2 : C::NTW;
-    auto kern = ddc_fused_w_kernel<D, JT, NEST>;
-    const size_t smem = C::HDR_BYTES + (size_t)C::NSLOT * C::SLOT_FLOATS * sizeof(float);
-    static bool attr_set[64] = {};
-    if (h->device < 64 && !attr_set[h->device]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[h->device] = true;
-    }
-    TapsParam<NT> tp;
-    // folded taps of the last (step, jt, D, nesting): streaming callers repeat the same step call after call
-    if (h->wt_jt != JT || h->wt_d != D || h->wt_nest != NEST || h->wt_step != step || h->wt_cache.size() != (size_t)NT) {
-        h->wt_cache.assign((size_t)NT, make_float2(0.f, 0.f));
-        if (NEST) make_w2taps(h, step, JT, D, h->wt_cache.data());
-        else make_wtaps(h, step, JT, D, h->wt_cache.data());
-        h->wt_step = step;
-        h->wt_jt = JT;
-        h->wt_d = D;
-        h->wt_nest = NEST;
-    }
-    std::memcpy(tp.c2, h->wt_cache.data(), sizeof(float2) * (size_t)NT);
-    const long long grid = std::min<long long>(p.total_tiles, h->sm_count);
-    kern<<<(unsigned)grid, C::NWARPS * 32 + 32 * C::NPROD, smem, st>>>(p, tp);
-    CUDA_TRY(cudaGetLastError());
-    h->launches++;
-    char name[96];
-    snprintf(name, sizeof(name), "fused_fast_fir%s<D%d,R%d,J%d,SLOTS%d>", NEST ? "_nested" : "", D, C::R, JT, C::NSLOT);
-    h->last_variant = name;
-    return DDCB200_OK;
-}
-
-template <int D, int JT>
-int launch_w2x(ddcb200* h, RunParams& p, cudaStream_t st, double step) {
-    using C = WCfg<D, JT>;
-    auto kern = ddc_fused_w2x_kernel<D, JT>;
-    const size_t smem = C::HDR_BYTES + (size_t)C::NSLOT * C::SLOT_FLOATS * sizeof(float);
-    static bool attr_set[64] = {};
-    if (h->device < 64 && !attr_set[h->device]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[h->device] = true;
-    }
-    TapsParam<C::NTW> tp;
-    std::memcpy(tp.c2, cached_wtaps(h, step, JT, D), sizeof(float2) * (size_t)C::NTW);
-    const long long grid = std::min<long long>(p.total_tiles, h->sm_count);
-    kern<<<(unsigned)grid, 2 * C::NWARPS * 32 + 32 * C::NPROD, smem, st>>>(p, tp);
-    CUDA_TRY(cudaGetLastError());
-    h->launches++;
-    char name[96];
-    snprintf(name, sizeof(name), "fused_fast_fir_16w<D%d,R%d,J%d,SLOTS%d>", D, C::R, JT, C::NSLOT);
-    h->last_variant = name;
-    return DDCB200_OK;
-}
-
-template <int D>
-int launch_w_j(ddcb200* h, RunParams& p, cudaStream_t st, double step, int jt, bool nest) {
-    if constexpr (D == 16) {   // two nested levels need R = 8 outputs per thread
-        // Experimental (option "variant" 9): measured SLOWER than one level -- 0.252 against 0.229 ms compute-only at
-        // T = 256 -- because each tap fetch then feeds only two FFMA2 (R / 4 outputs); kept for one configuration only.
-        if (nest && jt == 16) return launch_w<D, 16, 1>(h, p, st, step);
-    }
-    switch (jt) {
-        case 4: return launch_w<D, 4, 0>(h, p, st, step);
-        case 8: return launch_w<D, 8, 0>(h, p, st, step);
-        case 16: return launch_w<D, 16, 0>(h, p, st, step);
-        default: break;
-    }
-    if constexpr (D == 16) {   // long filters: passes of 16 tap blocks (T <= 1024)
-        if (jt == 32) return launch_w<D, 32, 0>(h, p, st, step);
-        if (jt == 64) return launch_w<D, 64, 0>(h, p, st, step);
-    }
-    return fail(DDCB200_EINVAL, "fast-FIR kernel: unsupported tap-block count %d at D = %d", jt, D);
-}
-
-template <int D, int JT>
-int launch_w10(ddcb200* h, RunParams& p, cudaStream_t st, double step) {
-    using C = W10Cfg<D, JT>;
-    auto kern = ddc_fused_w10_kernel<D, JT>;
-    const size_t smem = 512 + (size_t)C::FLOAT_BYTES + (size_t)C::NRAW * C::RAW_BYTES;
-    static bool attr_set[64] = {};
-    if (h->device < 64 && !attr_set[h->device]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[h->device] = true;
-    }
-    TapsParam<C::NTW> tp;
-    std::memcpy(tp.c2, cached_wtaps(h, step, JT, D), sizeof(float2) * (size_t)C::NTW);
-    const long long grid = std::min<long long>(p.total_tiles, h->sm_count);
-    kern<<<(unsigned)grid, C::NWARPS * 32 + 32 * C::NPROD, smem, st>>>(p, tp);
-    CUDA_TRY(cudaGetLastError());
-    h->launches++;
-    char name[96];
-    snprintf(name, sizeof(name), "fused_fast_fir_packed10<D%d,R%d,J%d,RAWSLOTS%d>", D, C::R, JT, C::NRAW);
-    h->last_variant = name;
-    return DDCB200_OK;
-}
-
-template <int D, int JT>
-int launch_w10s(ddcb200* h, RunParams& p, cudaStream_t st, double step) {
-    using C = W10SCfg<D, JT>;
-    auto kern = ddc_fused_w10s_kernel<D, JT>;
-    static bool attr_set[64] = {};
-    if (h->device < 64 && !attr_set[h->device]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        attr_set[h->device] = true;
-    }
-    TapsParam<C::NTW> tp;
-    std::memcpy(tp.c2, cached_wtaps(h, step, JT, D), sizeof(float2) * (size_t)C::NTW);
-    const long long grid = std::min<long long>(p.total_tiles, h->sm_count);
-    kern<<<(unsigned)grid, (C::NFIR + C::NUNP + 1) * 32, C::SMEM, st>>>(p, tp);
-    CUDA_TRY(cudaGetLastError());
-    h->launches++;
-    char name[112];
-    snprintf(name, sizeof(name), "fused_fast_fir_packed10_split<D%d,R%d,J%d,RAW%d,FLOAT%d,UNPACK%d>", D, C::R, JT, C::NR, C::NF, C::NUNP);
-    h->last_variant = name;
-    return DDCB200_OK;
-}
-
-template <int D>
-int launch_w10_j(ddcb200* h, RunParams& p, cudaStream_t st, double step, int jt) {
-    switch (jt) {
-        case 4: return launch_w10<D, 4>(h, p, st, step);
-        case 8: return launch_w10<D, 8>(h, p, st, step);
-        default: return launch_w10<D, 16>(h, p, st, step);
-    }
-}
-
-template <int JT, int NQ>
-int launch_wq(ddcb200* h, RunParams& p, cudaStream_t st, double step) {
-    using C = WQCfg<JT, NQ>;
-    auto kern = ddc_fused_wq_kernel<JT, NQ>;
-    const size_t smem = C::HDR_BYTES + (size_t)C::NSLOT * C::SLOT_FLOATS * sizeof(float);
-    static bool attr_set[64] = {};
-    if (h->device < 64 && !attr_set[h->device]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[h->device] = true;
-    }
-    static_assert(sizeof(TapsParam<C::NTW>) + sizeof(RunParams) <= 32764, "kernel parameter space");
-    TapsParam<C::NTW> tp;
-    if (h->wq_jt != JT || h->wq_nq != NQ || h->wq_step != step || h->wq_cache.size() != (size_t)C::NTW) {
-        h->wq_cache.resize((size_t)C::NTW);
-        make_wqtaps(h, step, JT, NQ, 16 / NQ, h->wq_cache.data());
-        h->wq_jt = JT;
-        h->wq_nq = NQ;
-        h->wq_step = step;
-    }
-    std::memcpy(tp.c2, h->wq_cache.data(), sizeof(float2) * (size_t)C::NTW);
-    const long long grid = std::min<long long>(p.total_tiles, h->sm_count);
-    kern<<<(unsigned)grid, C::NWARPS * 32 + 32 * C::NPROD, smem, st>>>(p, tp);
-    CUDA_TRY(cudaGetLastError());
-    h->launches++;
-    char name[96];
-    snprintf(name, sizeof(name), "fused_fast_fir_subfilters<D%d,NQ%d,J%d,SLOTS%d>", 16 / NQ, NQ, JT, C::NSLOT);
-    h->last_variant = name;
-    return DDCB200_OK;
-}
-
-// The small-decimation kernel is only instantiated where it was measured faster than the rotating-window tile kernel:
-// D = 8 with 513 .. 1048 taps (66 tap blocks), 0.495 against 0.545 ms at T = 1024, N = 2^26.  With fewer tap blocks the
-// tile kernel's 82-94 % FMA-pipe utilisation beats the 7 % net flop saving (profiles/r1_sweep_taps_decimation.md).
-template <int NQ>
-int launch_wq_j(ddcb200* h, RunParams& p, cudaStream_t st, double step, int jt) {
-    if constexpr (NQ == 2) {
-        if (jt == 66) return launch_wq<66, NQ>(h, p, st, step);
-    }
-    return fail(DDCB200_EINVAL, "small-decimation kernel: unsupported tap-block count %d", jt);
 }
 
 // ---- kernel WS (sliced staging, D = 32 / 64): tensor map over the input + launch -------------------------------------------
@@ -630,74 +186,65 @@ int make_slice_tmap(const float* d_in, int D, bool whole, int slot_rows, long lo
     if (r != CUDA_SUCCESS) return fail(DDCB200_ECUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
     return DDCB200_OK;
 }
-
-template <int D, int JT>
-int launch_ws(ddcb200* h, RunParams& p, const float* d_in, long long n_rows, cudaStream_t st, double step) {
-    using C = WSCfg<D, JT>;
-    auto kern = ddc_fused_ws_kernel<D, JT>;
-    static bool attr_set[64] = {};
-    if (h->device < 64 && !attr_set[h->device]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        // two CTAs per SM need the whole shared-memory carve-out (the driver's default follows ONE CTA's request)
-        if (C::CTAS > 1) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr_set[h->device] = true;
+int launch_ws(ddcb200* h, RunParams& p, const float* d_in, long long n_rows, cudaStream_t st, double step, int D, int jt) {
+    switch (D) {
+        case 4: return launch_ws4(h, p, d_in, n_rows, st, step, jt);
+        case 8: return launch_ws8(h, p, d_in, n_rows, st, step, jt);
+        case 16: return launch_ws16(h, p, d_in, n_rows, st, step, jt);
+        case 32: return launch_ws32(h, p, d_in, n_rows, st, step, jt);
+        case 64: return launch_ws64(h, p, d_in, n_rows, st, step, jt);
     }
-    p.cps_magic = p.tiles_per_stream > 1 ? ~0ull / (unsigned long long)p.tiles_per_stream + 1ull : 0ull;   // chunk_of()
-    CUtensorMap tmap;
-    int rc = make_slice_tmap(d_in, D, C::WHOLE, C::SLOT_ROWS, n_rows, p.n_streams, p.in_stride, &tmap);
-    if (rc) return rc;
-    TapsParam<C::NTW> tp;
-    std::memcpy(tp.c2, cached_wtaps(h, step, JT, D), sizeof(float2) * (size_t)C::NTW);
-    const long long grid = std::min<long long>(p.total_tiles, (long long)h->sm_count * C::CTAS);
-    kern<<<(unsigned)grid, C::NWARPS * 32 + 32 * C::NPROD, C::SMEM, st>>>(p, tmap, tp);
-    CUDA_TRY(cudaGetLastError());
-    h->launches++;
-    char name[96];
-    snprintf(name, sizeof(name), "fused_fast_fir_%s<D%d,R%d,J%d,SLICES%d,SLOTS%d>", D >= 32 ? "sliced" : (C::WHOLE ? "row_staged" : "tensor_staged"), D, C::R, JT, C::LPQ,
-             C::NSLOT);
-    h->last_variant = name;
+    return fail(DDCB200_EINVAL, "tensor-staged kernel: unsupported decimation %d", D);
+}
+}  // namespace ddch
+
+using ddch::make_ctaps;
+
+namespace {
+
+unsigned long long to_fx64(double frac01) {
+    // frac01 in [0,1) -> round(frac * 2^64) mod 2^64 using long double (64-bit mantissa on x86)
+    long double v = (long double)frac01 * 18446744073709551616.0L;
+    if (v >= 18446744073709551615.0L) return 0ull;
+    return (unsigned long long)(v + 0.5L);
+}
+
+unsigned long long phase_of(double step, int64_t sample_offset) {
+    // frac(sample_offset * step) * 2^64, exact modular arithmetic on the fixed-point step
+    const double fstep = step - std::floor(step);
+    const unsigned long long sfx = to_fx64(fstep);
+    return (unsigned long long)sample_offset * sfx;
+}
+
+int ensure_ring(ddcb200* h, int n_taps) {
+    if (n_taps <= h->ring_cap) return DDCB200_OK;
+    const int cap = std::max(n_taps, 1024);
+    for (int i = 0; i < ddcb200::kRing; ++i) {
+        if (h->d_ctaps[i]) cudaFree(h->d_ctaps[i]);
+        if (h->h_ctaps[i]) cudaFreeHost(h->h_ctaps[i]);
+        h->d_ctaps[i] = nullptr;
+        h->h_ctaps[i] = nullptr;
+        CUDA_TRY(cudaMalloc(&h->d_ctaps[i], sizeof(float2) * cap));
+        CUDA_TRY(cudaMallocHost(&h->h_ctaps[i], sizeof(float2) * cap));
+        if (!h->ring_ev[i]) CUDA_TRY(cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming));
+    }
+    h->ring_cap = cap;
     return DDCB200_OK;
 }
 
-// tap-block counts beyond 32 come in multiples of 16 (one more pass and two more halo rows each), up to WSCfg::JT_MAX
-template <int D, int JT>
-int launch_ws_from(ddcb200* h, RunParams& p, const float* d_in, long long n_rows, cudaStream_t st, double step, int jt) {
-    if (jt == JT) return launch_ws<D, JT>(h, p, d_in, n_rows, st, step);
-    if constexpr (JT + 16 <= WSCfg<D, 8>::JT_MAX) return launch_ws_from<D, JT + 16>(h, p, d_in, n_rows, st, step, jt);
-    return fail(DDCB200_EINVAL, "tensor-staged kernel: unsupported tap-block count %d at D = %d", jt, D);
+static inline bool aligned_f32(const void* d_in, int64_t in_stride, bool packed) {
+    return !packed && (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (in_stride % 4 == 0);
 }
 
-template <int D>
-int launch_ws_j(ddcb200* h, RunParams& p, const float* d_in, long long n_rows, cudaStream_t st, double step, int jt) {
-    switch (jt) {
-        case 8: return launch_ws<D, 8>(h, p, d_in, n_rows, st, step);
-        case 16: return launch_ws<D, 16>(h, p, d_in, n_rows, st, step);
-        default: return launch_ws_from<D, 32>(h, p, d_in, n_rows, st, step, jt);
-    }
-}
-
-template <int D>
-int launch_p_j(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, int jt, int ks) {
-    if (ks == 2) {
-        switch (jt) {
-            case 4: return launch_p<D, 4, 2>(h, p, ct, st);
-            case 8: return launch_p<D, 8, 2>(h, p, ct, st);
-            default: return launch_p<D, 16, 2>(h, p, ct, st);
-        }
-    }
-    switch (jt) {
-        case 4: return launch_p<D, 4, 1>(h, p, ct, st);
-        case 8: return launch_p<D, 8, 1>(h, p, ct, st);
-        default: return launch_p<D, 16, 1>(h, p, ct, st);
-    }
-}
-
-// Core dispatcher for device-resident data.
+// Core dispatcher for device-resident data.  Option "variant" (ddcb200_set_option): 0 auto; 1 generic kernel; 2 / 3 tile kernel
+// without / with the tap split; 5 direct-form packed kernel; 7 fast FIR (ddc_kernel_w.cuh, also for D = 32 / 64 and the
+// fused-unpack packed kernel); 8 phase-major direct form; 10 warp-specialised packed kernel; 11 tensor-staged / sliced fast FIR.
 int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int64_t n_streams, int64_t in_stride,
                double step, int64_t sample_offset, ddcb200_c64* d_out, int64_t out_stride, cudaStream_t st,
                int64_t m_limit = -1) {
     const int T = (int)h->taps.size();
     const int D = h->decim;
+    const int fv = h->force_variant;
     if (!d_in || !d_out) return fail(DDCB200_EINVAL, "null device pointer");
     if (n_streams <= 0 || n_samples <= 0) return fail(DDCB200_EINVAL, "n_samples and n_streams must be positive");
     if (n_samples < T) return fail(DDCB200_ETOOSHORT, "n_samples (%lld) < n_taps (%d)", (long long)n_samples, T);
@@ -723,66 +270,35 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
     p.l2_ahead = h->l2_ahead;
     p.dbg = h->d_dbg;
 
-    // ---- fused path eligibility ---------------------------------------------------------------------------
-    int R = 0;
-    switch (D) {
-        case 4: R = 16; break;
-        case 8: R = 8; break;
-        case 16: R = 4; break;
-        case 32: R = 2; break;
-        case 64: R = 1; break;
-        default: R = 0;
-    }
-    long long tiles = 0;
-    int n_taps_pad = T, J = 0, halo_rows = 0, ks = 1;
-    const bool aligned = !packed && (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (in_stride % 4 == 0);
-    if (R > 0 && aligned && h->force_variant != 1 && h->force_variant != 5 && h->force_variant != 6) {
-        J = (T + D - 1) / D;
-        // tap split 2 (16 compute warps) whenever it costs no extra zero taps; option "variant" 2 / 3 force KS 1 / 2
-        ks = (J % (2 * R) == 0 && R <= 4) ? 2 : 1;
-        if (h->force_variant == 2) ks = 1;
-        if (h->force_variant == 3 && R <= 4) ks = 2;
-        J = ((J + ks * R - 1) / (ks * R)) * (ks * R);  // each thread's tap-block loop is unrolled R times
-        n_taps_pad = J * D;
-        // a thread-row reads blocks 0 .. J+R-2 of its own row space -> rows g .. g + (J+R-2)/R
-        halo_rows = (J + R - 2) / R;
-        const long long tile_out = 256LL * R;
-        if (n_taps_pad <= kMaxTapsFused) tiles = (M + tile_out - 1) / tile_out;  // the last one may be ragged
-    }
-
-    // ---- packed 10-bit input: phase-major kernel with the unpack fused behind the TMA ring -------------------------
-    if (packed && (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (in_stride % 16 == 0) && (D == 16 || D == 32 || D == 64) &&
-        (T + D - 1) / D <= 16 && h->force_variant != 1) {
-        const int Jp = (T + D - 1) / D;
-        const int jt = Jp <= 4 ? 4 : (Jp <= 8 ? 8 : 16);
+    const int Jp = (T + D - 1) / D;   // tap blocks of D taps
+    const bool pow2_d = D == 4 || D == 8 || D == 16 || D == 32 || D == 64;
+    // ring kernels (ddc_kernel_p / _w / _w10.cuh): chunks of 32 thread-rows of 128 samples
+    auto ring_geometry = [&](int jt) {
         const long long chunk_out = 32LL * (128 / D);
         p.tiles_per_stream = (M + chunk_out - 1) / chunk_out;
         p.total_tiles = p.tiles_per_stream * n_streams;
         p.n_taps = jt * D;
         p.n_tap_blocks = jt;
         p.m_begin = 0;
-        // fast-FIR variant where a thread has R = 8 outputs (D = 16); option "variant" 7 forces it, 5 forces the direct form
-        // warp-specialised variant (unpack warps + FIR warps): 1.10 against 1.13 ms on 64 x 2^24 samples; default where it is
-        // instantiated (D = 16, 129 .. 256 taps); option "variant" 7 forces the fused-unpack kernel, 10 this one
-        if (D == 16 && jt == 16 && (h->force_variant == 10 || h->force_variant == 0)) return launch_w10s<16, 16>(h, p, st, step);
-        if ((D == 16 && h->force_variant != 5) || h->force_variant == 7) {
-            switch (D) {
-                case 16: return launch_w10_j<16>(h, p, st, step, jt);
-                case 32: return launch_w10_j<32>(h, p, st, step, jt);
-                default: return launch_w10_j<64>(h, p, st, step, jt);
-            }
-        }
+    };
+
+    // ---- packed 10-bit input with the unpack fused behind the TMA ring (D = 16 / 32 / 64, up to 16 tap blocks) --------
+    if (packed && (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (in_stride % 16 == 0) && (D == 16 || D == 32 || D == 64) &&
+        Jp <= 16 && fv != 1) {
+        const int jt = Jp <= 4 ? 4 : (Jp <= 8 ? 8 : 16);
+        ring_geometry(jt);
+        // warp-specialised kernel (unpack warps + FIR warps): 1.10 against 1.13 ms on 64 x 2^24 samples; default where it is
+        // instantiated (D = 16, 129 .. 256 taps).  Fast FIR with in-warp unpack where a thread has R = 8 outputs (D = 16), direct
+        // form at D = 32 / 64.
+        if (D == 16 && jt == 16 && (fv == 10 || fv == 0)) return ddch::launch_w10s(h, p, st, step);
+        if ((D == 16 && fv != 5) || fv == 7) return ddch::launch_w10(h, p, st, step, D, jt);
         std::vector<float2> ctp((size_t)jt * D);
         make_ctaps(h, step, jt * D, ctp.data());
-        switch (D) {
-            case 16: return launch_p10_j<16>(h, p, ctp.data(), st, jt);
-            case 32: return launch_p10_j<32>(h, p, ctp.data(), st, jt);
-            default: return launch_p10_j<64>(h, p, ctp.data(), st, jt);
-        }
+        return ddch::launch_p10(h, p, ctp.data(), st, D, jt);
     }
 
     // ---- packed input without a fused-unpack kernel for this (T, D): unpack into a float32 workspace, then the float32 path --
-    if (packed && h->force_variant != 1) {
+    if (packed && fv != 1) {
         const long long pitch = (n_samples + 3) / 4 * 4;
         const size_t need = (size_t)pitch * (size_t)n_streams;
         if (need > h->unpack_ws_cap) {
@@ -813,147 +329,98 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         return DDCB200_OK;
     }
 
-    // ---- large decimations (D = 32, 64): sliced staging (ddc_kernel_ws.cuh), fast FIR with R = 8 outputs per thread ----------
-    // Auto: where the direct form is FP32-bound (4 T / D flop per sample against 4 + 8 / D bytes at the measured ridge of
-    // 11.4 flop/B); HBM-bound cells stay on the phase-major kernel, which over-fetches nothing.  Option "variant" 11 forces it.
+    const bool aligned = aligned_f32(d_in, in_stride, packed);
     long long m_done = 0;
-    bool sliced_done = false;
-    {
-        const int Jp = (T + D - 1) / D;
+    bool fused_done = false;
+
+    // ---- tensor-staged fast FIR (ddc_kernel_ws.cuh), R = 8 outputs per thread at every decimation ------------------------------
+    //   D = 32 / 64: sliced staging, where the direct form is FP32-bound (4 T / D flop per sample against 4 + 8 / D bytes at the
+    //   measured ridge of 11.4 flop/B); HBM-bound cells stay on the phase-major kernel, which over-fetches nothing.
+    //   D = 4 / 8, up to 1024 taps: whole blocks, two CTAs per SM (sixteen compute warps) -- measured at N = 2^26 against the tile
+    //   kernel: D = 4: T = 64 0.085 vs 0.128 ms, 128 0.126 vs 0.173, 256 0.234 vs 0.274, 512 0.456 vs 0.503, 1024 0.895 vs 0.981;
+    //   D = 8: T = 64 0.054 vs 0.062, 128 0.070 vs 0.083, 256 0.122 vs 0.141, 512 0.229 vs 0.265, 1024 0.449 vs 0.545.
+    //   D = 16: whole-row tiles for the HBM-bound filters only (T <= 128: 0.0517 against 0.0524 / 0.0537 ms of the 1-D bulk-copy
+    //   kernel); longer filters are much slower here than in ddc_kernel_w.cuh (T = 256: 0.312 vs 0.244 ms at 2^28).
+    // The kernel pads the filter to 8, 16 or a multiple of 16 tap blocks, the tile kernel to a multiple of its R (16 / 8 at
+    // D = 4 / 8): auto only where the padded work is within 12 % of the tile kernel's (its deficit there: 84-94 % against 99 %).
+    if (aligned && pow2_d && fv != 1) {
+        const int r_tile = 64 / D;   // outputs per thread of the tile kernel
         const bool fp32_bound = 4.0 * T / D > 11.4 * (4.0 + 8.0 / D);
-        // D = 4 / 8 / 16: the same tensor-staged kernel with whole blocks (R = 8 outputs per thread), ddc_kernel_ws.cuh.
-        //   D = 4 / 8, up to 1024 taps: two CTAs per SM (sixteen compute warps; WSCfg::CTAS) -- measured at N = 2^26 against the tile
-        //   kernel: D = 4: T = 64 0.085 vs 0.128 ms, 128 0.126 vs 0.173, 256 0.234 vs 0.274, 512 0.456 vs 0.503, 1024 0.895 vs 0.981;
-        //   D = 8: T = 64 0.054 vs 0.062, 128 0.070 vs 0.083, 256 0.122 vs 0.141, 512 0.229 vs 0.265, 1024 0.449 vs 0.495 (sub-filter
-        //   kernel).  Padded taps <= 64 use whole-row tiles (WSCfg::WHOLE).
-        //   D = 16: whole-row tiles for the HBM-bound filters only (T <= 128: 0.0517 against 0.0524 / 0.0537 ms of the 1-D bulk-copy
-        //   kernel); longer filters are much slower here than in ddc_kernel_w.cuh (T = 256: 0.312 vs 0.244 ms at 2^28): option 11.
-        // The kernel pads the filter to 8, 16 or a multiple of 16 tap blocks, the tile kernel to a multiple of its R (16 / 8 at
-        // D = 4 / 8): auto only where the padded work is within 12 % of the tile kernel's (its deficit there: 84-94 % against 99 %).
         const int jt_ws = Jp <= 8 ? 8 : (Jp + 15) / 16 * 16;
-        const int j_tile = R > 0 ? (Jp + R - 1) / R * R : Jp;
+        const int j_tile = (Jp + r_tile - 1) / r_tile * r_tile;
         const bool pad_ok = jt_ws * 100 <= j_tile * 112;
-        const bool small_auto = (D == 4 && T <= 1024 && pad_ok) || (D == 8 && T <= 1024 && pad_ok) || (D == 16 && T <= 128);
-        const bool small_d = (D == 4 || D == 8 || D == 16) && (h->force_variant == 11 || (h->force_variant == 0 && small_auto));
-        if (aligned_f32(d_in, in_stride, packed) && Jp <= (D == 4 ? 256 : (D == 8 ? 128 : 32)) && T >= D &&
-            (small_d || ((D == 32 || D == 64) && (h->force_variant == 11 || (h->force_variant == 0 && fp32_bound))))) {
-            const int jt = jt_ws;
+        const bool auto_ws = (D == 4 && T <= 1024 && pad_ok) || (D == 8 && T <= 1024 && pad_ok) || (D == 16 && T <= 128) ||
+                             ((D == 32 || D == 64) && fp32_bound);
+        if (Jp <= (D == 4 ? 256 : (D == 8 ? 128 : 32)) && T >= D && (fv == 11 || (fv == 0 && auto_ws))) {
             const long long n_blocks = (n_samples / (8LL * D)) * 8;         // whole thread-rows of 8 blocks: the tensor map covers exactly these
             long long m_f = n_blocks * D >= T ? (n_blocks * D - T) / D + 1 : 0;   // outputs whose window lies inside them
             if (m_f > M) m_f = M;
             // chunk_of() divides by multiplication: exact while total chunks x chunks per stream < 2^64
             if ((double)((m_f + 255) / 256) * (double)((m_f + 255) / 256) * (double)n_streams >= 1.8e19) m_f = 0;
             if (m_f > 0) {
-                const long long m_all = p.n_out;
                 p.n_out = m_f;
                 p.tiles_per_stream = (m_f + 255) / 256;
                 p.total_tiles = p.tiles_per_stream * n_streams;
-                p.n_taps = jt * D;
-                p.n_tap_blocks = jt;
+                p.n_taps = jt_ws * D;
+                p.n_tap_blocks = jt_ws;
                 p.m_begin = 0;
-                const float* fin = reinterpret_cast<const float*>(d_in);
-                int rc2 = D == 4    ? launch_ws_j<4>(h, p, fin, n_blocks / 8, st, step, jt)
-                          : D == 8  ? launch_ws_j<8>(h, p, fin, n_blocks / 8, st, step, jt)
-                          : D == 16 ? launch_ws_j<16>(h, p, fin, n_blocks / 8, st, step, jt)
-                          : D == 32 ? launch_ws_j<32>(h, p, fin, n_blocks / 8, st, step, jt)
-                                    : launch_ws_j<64>(h, p, fin, n_blocks / 8, st, step, jt);
+                int rc2 = ddch::launch_ws(h, p, reinterpret_cast<const float*>(d_in), n_blocks / 8, st, step, D, jt_ws);
                 if (rc2) return rc2;
-                p.n_out = m_all;
-                m_done = m_f;
-                sliced_done = true;
+                p.n_out = M;
+                m_done = m_f;      // the few outputs that need the last partial thread-row come from the generic kernel below
+                fused_done = true;
             }
         }
     }
 
-    // ---- small decimations (D = 4, 8): NQ = 16 / D interleaved decimate-by-16 fast FIRs with shifted tap sets --------------
-    if (!sliced_done && aligned_f32(d_in, in_stride, packed) && (D == 4 || D == 8) && (h->force_variant == 0 || h->force_variant == 7)) {
-        const int nq = 16 / D;
-        const int Tq = T + D * (nq - 1);
-        const int jneed = (Tq + 15) / 16;
-        const int jt = (nq == 2 && jneed > 34 && jneed <= 66) ? 66 : 0;   // see launch_wq_j
-        if (jt) {
-            const long long mq = (M + nq - 1) / nq;           // decimate-by-16 outputs per tap set
-            p.tiles_per_stream = (mq + 255) / 256;
-            p.total_tiles = p.tiles_per_stream * n_streams;
-            p.n_taps = jt * 16;
-            p.n_tap_blocks = jt;
-            p.m_begin = 0;
-            return nq == 2 ? launch_wq_j<2>(h, p, st, step, jt) : launch_wq_j<4>(h, p, st, step, jt);
-        }
-    }
-
-    // ---- kernel P (phase-major, R = 128/D outputs per thread): short polyphase branches, J = ceil(T/D) <= 16 ------
-    const bool long_w = D == 16 && (T + D - 1) / D > 16 && (T + D - 1) / D <= 64 &&
-                        (h->force_variant == 0 || h->force_variant == 7 || h->force_variant == 9);
-    if (!sliced_done && aligned_f32(d_in, in_stride, packed) && (D == 16 || D == 32 || D == 64) && ((T + D - 1) / D <= 16 || long_w) &&
-        (h->force_variant == 0 || (h->force_variant >= 5 && h->force_variant <= 9) || h->force_variant == 12)) {
-        const int ksp = (h->force_variant == 6) ? 2 : 1;   // option "variant": 5 (= auto) one warp per chunk, 6 = two (slower)
-        const int Jp = (T + D - 1) / D;
+    // ---- ring kernels on 1-D bulk copies: fast FIR (D = 16, up to 64 tap blocks) / phase-major direct form (D = 32, 64) -----
+    if (!fused_done && aligned && (D == 16 || D == 32 || D == 64) && (Jp <= 16 || (D == 16 && Jp <= 64)) &&
+        (fv == 0 || fv == 7 || fv == 8)) {
         const int jt = Jp <= 4 ? 4 : (Jp <= 8 ? 8 : (Jp <= 16 ? 16 : (Jp <= 32 ? 32 : 64)));
-        const long long chunk_out = 32LL * (128 / D);   // PCfg::CHUNK_OUT
-        p.tiles_per_stream = (M + chunk_out - 1) / chunk_out;
-        p.total_tiles = p.tiles_per_stream * n_streams;
-        p.n_taps = jt * D;
-        p.n_tap_blocks = jt;
-        p.m_begin = 0;
-        // option "variant": 0 auto; 5 / 6 kernel P with one / two warps per chunk; 7 fast FIR (kernel W); 8 deferred-epilogue P.
-        // Auto picks the fast-FIR kernel where a thread has R = 8 outputs (D = 16) and the output rows allow 16-byte stores.
-        if (h->force_variant == 12 && D == 16 && jt == 16) return launch_w2x<16, 16>(h, p, st, step);   // 16 compute warps (experiment)
-        const bool want_w = h->force_variant == 7 || h->force_variant == 9 || (h->force_variant == 0 && D == 16);
-        if (want_w) {   // any complex64-aligned output: the epilogue picks its 16-byte pairing per thread
-            const bool nest = h->force_variant == 9;   // option "variant" 9: two nested fast-FIR levels (D = 16)
-            switch (D) {
-                case 16: return launch_w_j<16>(h, p, st, step, jt, nest);
-                case 32: return launch_w_j<32>(h, p, st, step, jt, nest);
-                default: return launch_w_j<64>(h, p, st, step, jt, nest);
-            }
-        }
+        ring_geometry(jt);
+        // the fast-FIR kernel where a thread has R = 8 outputs (D = 16); any complex64-aligned output: its epilogue picks the
+        // 16-byte store pairing per thread
+        if (fv == 7 || (fv == 0 && D == 16) || jt > 16) return ddch::launch_w(h, p, st, step, D, jt);
         std::vector<float2> ctp((size_t)jt * D);
         make_ctaps(h, step, jt * D, ctp.data());
-        if (h->force_variant == 0 || h->force_variant == 8) {   // deferred-epilogue variant
-            switch (D) {
-                case 16: return launch_pd_j<16>(h, p, ctp.data(), st, jt);
-                case 32: return launch_pd_j<32>(h, p, ctp.data(), st, jt);
-                default: return launch_pd_j<64>(h, p, ctp.data(), st, jt);
-            }
-        }
-        switch (D) {
-            case 16: return launch_p_j<16>(h, p, ctp.data(), st, jt, ksp);
-            case 32: return launch_p_j<32>(h, p, ctp.data(), st, jt, ksp);
-            default: return launch_p_j<64>(h, p, ctp.data(), st, jt, ksp);
+        return ddch::launch_pd(h, p, ctp.data(), st, D, jt);
+    }
+
+    // ---- rotating-window tile kernel: any tap count up to 2048 at D = 4 .. 64 ---------------------------------------------------
+    int n_taps_pad = T;
+    if (!fused_done && aligned && pow2_d && fv != 1) {
+        const int R = 64 / D;
+        // tap split 2 (16 compute warps) whenever it costs no extra zero taps; option "variant" 2 / 3 force KS 1 / 2
+        int ks = (Jp % (2 * R) == 0 && R <= 4) ? 2 : 1;
+        if (fv == 2) ks = 1;
+        if (fv == 3 && R <= 4) ks = 2;
+        const int J = ((Jp + ks * R - 1) / (ks * R)) * (ks * R);  // each thread's tap-block loop is unrolled R times
+        if (J * D <= 2048) {
+            n_taps_pad = J * D;
+            std::vector<float2> ct((size_t)n_taps_pad);
+            make_ctaps(h, step, n_taps_pad, ct.data());
+            const long long tile_out = 256LL * R;
+            p.tiles_per_stream = (M + tile_out - 1) / tile_out;   // the last one may be ragged
+            p.total_tiles = p.tiles_per_stream * n_streams;
+            p.n_taps = n_taps_pad;
+            p.n_tap_blocks = J;
+            p.halo_rows = (J + R - 2) / R;   // a thread-row reads blocks 0 .. J+R-2 of its own row space
+            p.m_begin = 0;
+            int rc2 = ddch::launch_tile(h, p, ct.data(), st, D, ks);
+            if (rc2) return rc2;
+            m_done = M;
+            fused_done = true;
         }
     }
 
-    std::vector<float2> ct((size_t)std::max(n_taps_pad, T));
-    make_ctaps(h, step, (int)ct.size(), ct.data());
-
-    int rc = DDCB200_OK;
-    if (tiles > 0 && !sliced_done) {
-        p.tiles_per_stream = tiles;
-        p.total_tiles = tiles * n_streams;
-        p.n_taps = n_taps_pad;
-        p.n_tap_blocks = J;
-        p.halo_rows = halo_rows;
-        p.m_begin = 0;
-        const int grid_limit = h->sm_count;
-        switch (D) {
-            case 4: rc = launch_fused_t<4, 16>(h, p, ct.data(), st, grid_limit, ks); break;
-            case 8: rc = launch_fused_t<8, 8>(h, p, ct.data(), st, grid_limit, ks); break;
-            case 16: rc = launch_fused_t<16, 4>(h, p, ct.data(), st, grid_limit, ks); break;
-            case 32: rc = launch_fused_t<32, 2>(h, p, ct.data(), st, grid_limit, ks); break;
-            case 64: rc = launch_fused_t<64, 1>(h, p, ct.data(), st, grid_limit, ks); break;
-        }
-        if (rc) return rc;
-        m_done = M;
-    }
     if (m_done < M) {
-        // stream tails / everything the fused path does not cover
-        rc = ensure_ring(h, T);
+        // stream tails / everything the fused kernels do not cover (odd decimations, unaligned rows, more than 2048 taps)
+        int rc = ensure_ring(h, T);
         if (rc) return rc;
         const int slot = h->ring_pos;
         h->ring_pos = (h->ring_pos + 1) % ddcb200::kRing;
         CUDA_TRY(cudaEventSynchronize(h->ring_ev[slot]));  // previous user of this slot has consumed it
-        std::memcpy(h->h_ctaps[slot], ct.data(), sizeof(float2) * T);
+        make_ctaps(h, step, T, h->h_ctaps[slot]);
         CUDA_TRY(cudaMemcpyAsync(h->d_ctaps[slot], h->h_ctaps[slot], sizeof(float2) * T, cudaMemcpyHostToDevice, st));
         p.n_taps = T;
         p.m_begin = m_done;
@@ -966,7 +433,7 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(h->ring_ev[slot], st));
         h->launches++;
-        if (tiles == 0 && !sliced_done) h->last_variant = packed ? "generic<packed10>" : "generic<f32>";
+        if (!fused_done) h->last_variant = packed ? "generic<packed10>" : "generic<f32>";
     }
     return DDCB200_OK;
 }
@@ -1174,7 +641,7 @@ int run_host(ddcb200* h, const void* h_in, bool packed, int64_t n_samples, int64
 extern "C" {
 
 int ddcb200_version(void) { return DDCB200_VERSION; }
-const char* ddcb200_last_error(void) { return g_err; }
+const char* ddcb200_last_error(void) { return ddch::g_err; }
 
 int64_t ddcb200_out_len(int64_t n_samples, int n_taps, int decimation) {
     if (n_samples <= 0 || n_taps <= 0 || decimation <= 0) return 0;
@@ -1190,7 +657,6 @@ int ddcb200_set_taps(ddcb200_t* h, const double* taps, int n_taps) {
     h->taps.assign(taps, taps + n_taps);
     h->taps_sum = s;
     h->wt_jt = 0;   // invalidate the folded-tap caches
-    h->wq_jt = 0;
     return DDCB200_OK;
 }
 

@@ -1,0 +1,7 @@
+#include "k_ws.inc"
+
+namespace ddch {
+int launch_ws4(ddcb200* h, RunParams& p, const float* d_in, long long n_rows, cudaStream_t st, double step, int jt) {
+    return launch_ws_j<4>(h, p, d_in, n_rows, st, step, jt);
+}
+}  // namespace ddch

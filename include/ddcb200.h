@@ -181,9 +181,9 @@ int64_t ddcb200_launch_count(ddcb200_t* handle);
 /* Name of the kernel variant the last run on this handle dispatched to (e.g. "fused_tma<D16,R4,T256>"). */
 const char* ddcb200_last_variant(ddcb200_t* handle);
 /* Tuning/diagnostic knobs (all optional; 0 restores the default):
- *   "variant"        kernel choice: 0 auto, 1 generic, 2/3 tile kernel, 5/6 phase-major direct form, 7 fast FIR, 8 deferred-
- *                    epilogue direct form, 9 nested fast FIR, 10 warp-specialised packed kernel, 11 tensor-staged / sliced
- *                    fast FIR, 12 sixteen-compute-warp fast FIR (see DESIGN.md section 4 and tools/README.md);
+ *   "variant"        kernel choice: 0 auto, 1 generic, 2 / 3 tile kernel without / with the tap split, 5 direct-form packed
+ *                    kernel, 7 fast FIR on 1-D bulk copies, 8 phase-major direct form, 10 warp-specialised packed kernel,
+ *                    11 tensor-staged / sliced fast FIR (see DESIGN.md section 4 and tools/README.md);
  *   "chunk_samples"  time-chunk size of the host path (default 2^24 samples per launch);
  *   "copy_threads"   host threads that stage pageable input through pinned buffers and widen complex128 output (default 4,
  *                    0 = leave pageable copies to the driver);
