@@ -65,6 +65,19 @@ struct ddcb200 {
     float* d_unpack_ws = nullptr;          // float32 workspace of the two-launch packed path (unpack, then a float32 kernel)
     size_t unpack_ws_cap = 0;
     cudaEvent_t unpack_ev = nullptr;       // end of the last kernel that read the workspace (calls may come on different streams)
+    // tensor-core engine for packed input (ddc_kernel_tc.cuh): fp16 hi / lo tap-matrix images, device ring + cache key
+    static constexpr int kTcRing = 4;
+    void* d_tc_b[kTcRing] = {};
+    void* h_tc_b[kTcRing] = {};            // pinned
+    size_t tc_cap[kTcRing] = {};
+    cudaEvent_t tc_ev[kTcRing] = {};       // end of the last kernel that read each image
+    cudaEvent_t tc_up_ev = nullptr;        // end of the last upload
+    int tc_slot = -1, tc_d = 0;
+    double tc_step = 0.0;
+    unsigned long long taps_version = 0, tc_version = 0;
+    float tc_inv_scale = 1.f, tc_lo_scale = 1.f;
+    int tc_ns = 0, tc_ns_built = 0;        // option "tc_ns": force the sub-stream count (tuning); the one of the cached image
+    int packed_engine = 0;                 // option "packed_engine": 0 CUDA cores (default), 1 tensor cores where supported
     ddcb200_c64* h_ostage[kBufs] = {};   // pinned landing buffers for the complex128 host path (one per chunk buffer)
     size_t ostage_cap = 0;
 };
@@ -87,6 +100,8 @@ int launch_p10(ddcb200* h, RunParams& p, const float2* ctaps, cudaStream_t st, i
 int launch_w(ddcb200* h, RunParams& p, cudaStream_t st, double step, int D, int jt);                                  // k_w.cu
 int launch_w10(ddcb200* h, RunParams& p, cudaStream_t st, double step, int D, int jt);                                // k_w10.cu
 int launch_w10s(ddcb200* h, RunParams& p, cudaStream_t st, double step);                                              // k_w10.cu
+bool tc10_supported(const ddcb200* h, int n_taps, int D);                                                                               // k_tc.cu
+int launch_tc10(ddcb200* h, RunParams& p, cudaStream_t st, double step, int D);                                       // k_tc.cu
 int launch_ws(ddcb200* h, RunParams& p, const float* d_in, long long n_rows, cudaStream_t st, double step, int D, int jt);   // k_ws*.cu
 int launch_ws4(ddcb200* h, RunParams& p, const float* d_in, long long n_rows, cudaStream_t st, double step, int jt);
 int launch_ws8(ddcb200* h, RunParams& p, const float* d_in, long long n_rows, cudaStream_t st, double step, int jt);

@@ -282,6 +282,12 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         p.m_begin = 0;
     };
 
+    // ---- packed 10-bit input on the tensor cores (opt-in: option "packed_engine" = 1 or "variant" = 13; ddc_kernel_tc.cuh) ---
+    if (packed && (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (in_stride % 16 == 0) && pow2_d &&
+        (fv == 13 || (fv == 0 && h->packed_engine == 1)) && ddch::tc10_supported(h, T, D) &&
+        (double)((M + 127) / 128) * (double)n_streams < 2.0e9)
+        return ddch::launch_tc10(h, p, st, step, D);
+
     // ---- packed 10-bit input with the unpack fused behind the TMA ring (D = 16 / 32 / 64, up to 16 tap blocks) --------
     if (packed && (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (in_stride % 16 == 0) && (D == 16 || D == 32 || D == 64) &&
         Jp <= 16 && fv != 1) {
@@ -657,6 +663,7 @@ int ddcb200_set_taps(ddcb200_t* h, const double* taps, int n_taps) {
     h->taps.assign(taps, taps + n_taps);
     h->taps_sum = s;
     h->wt_jt = 0;   // invalidate the folded-tap caches
+    h->taps_version++;
     return DDCB200_OK;
 }
 
@@ -716,6 +723,12 @@ void ddcb200_destroy(ddcb200_t* h) {
         if (h->h_ostage[i]) cudaFreeHost(h->h_ostage[i]);
     if (h->d_unpack_ws) cudaFree(h->d_unpack_ws);
     if (h->unpack_ev) cudaEventDestroy(h->unpack_ev);
+    for (int i = 0; i < ddcb200::kTcRing; ++i) {
+        if (h->d_tc_b[i]) cudaFree(h->d_tc_b[i]);
+        if (h->h_tc_b[i]) cudaFreeHost(h->h_tc_b[i]);
+        if (h->tc_ev[i]) cudaEventDestroy(h->tc_ev[i]);
+    }
+    if (h->tc_up_ev) cudaEventDestroy(h->tc_up_ev);
     for (int i = 0; i < ddcb200::kBufs; ++i) {
         if (h->d_chunk_in[i]) cudaFree(h->d_chunk_in[i]);
         if (h->d_chunk_out[i]) cudaFree(h->d_chunk_out[i]);
@@ -955,17 +968,34 @@ int ddcb200_set_option(ddcb200_t* h, const char* key, int64_t value) {
     if (!strcmp(key, "dbg_counters")) {   // 1: allocate + zero, 0: free, 2: print wait/total cycle ratio to stderr
         DeviceGuard g(h->device);
         if (value == 1) {
-            if (!h->d_dbg) CUDA_TRY(cudaMalloc(&h->d_dbg, 64));
-            CUDA_TRY(cudaMemset(h->d_dbg, 0, 64));
+            if (!h->d_dbg) CUDA_TRY(cudaMalloc(&h->d_dbg, 128));
+            CUDA_TRY(cudaMemset(h->d_dbg, 0, 128));
         } else if (value == 2 && h->d_dbg) {
             unsigned long long v[2] = {0, 0};
             CUDA_TRY(cudaDeviceSynchronize());
             CUDA_TRY(cudaMemcpy(v, h->d_dbg, 16, cudaMemcpyDeviceToHost));
             fprintf(stderr, "dbg_counters: compute warps waited %llu of %llu cycles = %.2f %%\n", v[0], v[1], v[1] ? 100.0 * v[0] / v[1] : 0.0);
+            unsigned long long w[12] = {};
+            CUDA_TRY(cudaMemcpy(w, h->d_dbg + 2, sizeof(w), cudaMemcpyDeviceToHost));
+            static const char* role[4] = {"producer (raw_empty, -)", "mma (a_full, acc_empty)", "epilogue (acc_full, -)", "unpack (raw_full, a_empty)"};
+            for (int r = 0; r < 4; ++r)
+                if (w[3 * r + 2])
+                    fprintf(stderr, "dbg_counters: tensor engine %-28s waits %.1f %% + %.1f %% of %llu cycles\n", role[r],
+                            100.0 * w[3 * r] / w[3 * r + 2], 100.0 * w[3 * r + 1] / w[3 * r + 2], w[3 * r + 2]);
         } else if (value == 0 && h->d_dbg) {
             cudaFree(h->d_dbg);
             h->d_dbg = nullptr;
         }
+        return DDCB200_OK;
+    }
+    if (!strcmp(key, "packed_engine")) {   // 0: CUDA cores (default); 1: tcgen05 tensor cores for packed 10-bit input
+        if (value != 0 && value != 1) return fail(DDCB200_EINVAL, "packed_engine must be 0 or 1");
+        h->packed_engine = (int)value;
+        return DDCB200_OK;
+    }
+    if (!strcmp(key, "tc_ns")) {   // tuning: sub-streams of the tensor engine (0 = automatic)
+        if (value != 0 && value != 8 && value != 16 && value != 32) return fail(DDCB200_EINVAL, "tc_ns must be 0, 8, 16 or 32");
+        h->tc_ns = (int)value;
         return DDCB200_OK;
     }
     if (!strcmp(key, "l2_ahead")) {

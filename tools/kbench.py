@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--dbg", action="store_true", help="print the kernels' wait / total cycle counters (option dbg_counters)")
     ap.add_argument("--option", action="append", default=[], help="key=value passed to ddcb200_set_option")
     a = ap.parse_args()
     n = int(eval(a.samples))
@@ -51,6 +52,8 @@ def main():
     for _ in range(a.warmup):
         ddc.run_tensor(x, 100e6, out=out, packed=a.packed)
     torch.cuda.synchronize()
+    if a.dbg:
+        ddc.set_option("dbg_counters", 1)
     ts = []
     for _ in range(a.iters):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -59,6 +62,8 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
+    if a.dbg:
+        ddc.set_option("dbg_counters", 2)
     ms = float(np.median(ts))
     tot = a.streams * n
     bytes_ = tot * ((1.25 if a.packed else 4.0) + 8.0 / a.decim)
