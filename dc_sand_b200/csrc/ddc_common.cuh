@@ -201,6 +201,21 @@ __device__ __forceinline__ void mbar_wait_uni(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// one poll, warp-uniform result: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test_uni(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "vote.sync.all.pred q, p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, q;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // global -> shared bulk copy (SASS: UBLKCP), completion counted in bytes on `bar`
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

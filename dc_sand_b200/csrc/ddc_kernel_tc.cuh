@@ -33,8 +33,37 @@
 #ifndef DDCB200_TC_NUNP
 #define DDCB200_TC_NUNP 12
 #endif
+#ifndef DDCB200_TC_UB
+#define DDCB200_TC_UB 3
+#endif
+#ifndef DDCB200_TC_SLEEP_NS
+#define DDCB200_TC_SLEEP_NS 0
+#endif
 
 namespace ddck {
+
+// wait of a warp with slack in its schedule (producer, epilogue): back off between polls so that the spin does not take issue
+// slots and shared-memory transactions from the unpack warps
+__device__ __forceinline__ void mbar_wait_uni_sleep(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "vote.sync.all.pred q, p, 0xffffffff;\n"
+        "@q bra.uni DONE_%=;\n"
+        "nanosleep.u32 %2;\n"
+        "bra.uni WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(DDCB200_TC_SLEEP_NS)
+        : "memory");
+}
+#if DDCB200_TC_SLEEP_NS > 0
+#define TC_WAIT_SLACK(bar, par) mbar_wait_uni_sleep(bar, par)
+#else
+#define TC_WAIT_SLACK(bar, par) mbar_wait_uni(bar, par)
+#endif
 
 struct TcParams {
     const void* b_mat;        // fp16 B operand in its shared-memory image: [K / 8][N][8] halves
@@ -48,8 +77,9 @@ struct TcParams {
     int n_groups;             // 16-sample groups unpacked per tile
     int n_a;                  // A stages
     int n_raw;                // raw slots
-    float inv_scale;          // 1 / S
-    float lo_scale;           // 2^-11 / S
+    float inv_scale;          // 512 / S  (the unpack delivers v / 512)
+    float lo_scale;           // 512 * 2^-11 / S
+    uint32_t unp_mul[2];      // 2^10, 2^14: multipliers of the unpack (kept in the parameter block on purpose)
 };
 
 template <int NS_>
@@ -60,6 +90,7 @@ struct TcShape {
     static constexpr int TILE_S = TILE_ROWS * ROW_S;      // samples per tile
     static constexpr int TILE_PACKED = TILE_S / 4 * 5;    // packed bytes per tile
     static constexpr int NUNP = DDCB200_TC_NUNP;          // unpack warps
+    static constexpr int UNP_BATCH = DDCB200_TC_UB;       // 16-sample groups a lane unpacks per batch
     static constexpr int NTHREADS = (8 + NUNP) * 32;
     static constexpr int HDR = 1024;
     static constexpr int LOG_NS = NS == 8 ? 3 : (NS == 16 ? 4 : 5);
@@ -111,7 +142,57 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+// 16 lanes x 256 bits per block of eight columns, like an MMA accumulator fragment: lane t of the warp receives, for block q,
+// (row t / 4, columns 8 q + 2 (t % 4) + {0, 1}) in v[4 q + {0, 1}] and (row t / 4 + 8, same columns) in v[4 q + {2, 3}]
+__device__ __forceinline__ void tc_ld_16x256_x4(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld_16x256_x2(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+// Accumulator column of part c4 (0 re_hi, 1 re_lo, 2 im_hi, 3 im_lo) of output r of a row with R outputs.  With R >= 4 the
+// columns are ordered for the 16x256b fragment load: lane t % 4 = j then owns ALL FOUR parts of outputs 2 j and 2 j + 1 of a
+// row (of output j when R = 4), so a quad of lanes writes 64 (32) contiguous bytes and the eight quads of a warp store eight
+// consecutive rows -- whole sectors, where the row-per-lane 32x32b load gives 16-byte pieces 64 bytes apart.
+__host__ __device__ constexpr int tc_col(int R, int r, int c4) {
+    return R >= 8 ? 32 * (r / 8) + 8 * (2 * (r % 2) + c4 / 2) + 2 * ((r % 8) / 2) + (c4 % 2)
+                  : (R == 4 ? 8 * (c4 / 2) + 2 * r + (c4 % 2) : 4 * r + c4);
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 16 packed samples (five little-endian words of the big-endian bit stream: sample s = bits [10 s, 10 s + 10) from the top) ->
+// eight fp16 pairs holding v / 512, bit-exact.  Per pair q (samples 2q, 2q+1 = 20 bits from bit 20 q, i.e. three bytes from byte
+// 5q / 2): one PRMT gathers the three bytes, most significant first, from the little-endian words; one LOP3 flips the two sign
+// bits (offset binary u = v + 512) and isolates the pair; one 32 x 32 -> 64 bit multiply by a power of two (IMAD.WIDE on the FMA
+// pipe; the multipliers come from the parameter block so that ptxas keeps the multiply instead of ALU-pipe shifts) leaves u_a in
+// the high word and u_b in the top ten bits of the low word; one shift-add (LEA.HI) drops u_b into the high half.  Each half
+// now holds u as an fp16 DENORMAL (u 2^-24), and one HFMA2 finishes: u 2^-24 * 2^15 - 1 = (u - 512) / 512 = v / 512, exact.
+// 4 instructions per pair, 2 on the ALU pipe and 2 on the FMA pipe; the factor 512 goes into the epilogue's scales.
+__device__ __forceinline__ void tc_unpack16(const uint32_t (&rw)[5], uint32_t (&h)[8], const TcParams& tc) {
+    const __half2 k15 = __floats2half2_rn(32768.f, 32768.f), m1 = __floats2half2_rn(-1.f, -1.f);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int bo = (20 * q) >> 3, wi = bo >> 2, j0 = bo & 3, s2 = (20 * q) & 7;   // s2 = 0 or 4
+        const int j2 = j0 + 2 > 7 ? 7 : j0 + 2;
+        const uint32_t sel = (uint32_t)((j0 << 12) | ((j0 + 1) << 8) | (j2 << 4) | j2);
+        const uint32_t src = __byte_perm(rw[wi], rw[wi + 1 > 4 ? 4 : wi + 1], sel);
+        uint32_t fm;
+        asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(fm) : "r"(src), "r"(0x80200000u >> s2), "r"(0xFFFFF000u >> s2));   // (src ^ x) & m
+        uint32_t plo, phi;
+        asm("{\n.reg .b64 t;\nmul.wide.u32 t, %2, %3;\nmov.b64 {%0, %1}, t;\n}" : "=r"(plo), "=r"(phi) : "r"(fm), "r"(tc.unp_mul[s2 >> 2]));
+        const uint32_t w = phi + (plo >> 6);
+        const __half2 hv = __hfma2(*reinterpret_cast<const __half2*>(&w), k15, m1);
+        h[q] = *reinterpret_cast<const uint32_t*>(&hv);
+    }
+}
 
 template <int D, int NS>
 __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(const __grid_constant__ RunParams p,
@@ -185,7 +266,7 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
         uint32_t par = 1;   // first pass: the slots are free
         for (int k = 0; k < n_k; ++k) {
             const long long t0 = p.dbg ? clock64() : 0;
-            mbar_wait_uni(&raw_empty[slot], par);
+            TC_WAIT_SLACK(&raw_empty[slot], par);
             if (p.dbg) tw0 += clock64() - t0;
             const unsigned char* src = reinterpret_cast<const unsigned char*>(p.in) + (long long)cs * p.in_stride + (long long)cc * S::TILE_PACKED;
             unsigned char* dst = rsm + (size_t)slot * tc.raw_slot_bytes;
@@ -252,32 +333,114 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
             acc ^= 1;
             if (acc == 0) cpar ^= 1u;
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ------------------------------------------------------------------ epilogue warps: TMEM lanes 32 (warp % 4) ..
-        const int row = (warp & 3) * 32 + lane;
-        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    } else if (warp >= 4 && warp < 8 && R >= 4) {
+        // ------------------------------------------------------------------ epilogue warps (four or more outputs per row):
+        // fragment loads, lane (i, j) = (lane / 4, lane % 4) handles rows quad * 32 + i + 8 h, h = 0 .. 3, outputs 2 j, 2 j + 1
+        // of every 32-column block (output j when R = 4).
+        // NCO: the tap matrix carries the rotation by the sample's position INSIDE the row (k_tc.cu: build_b), so every output
+        // of a row takes the same residual rotation e^{-j 2 pi step (first sample of the row)}: one polynomial rotation (64-bit
+        // fixed-point phase) per thread and tile, three angle-addition steps for its other rows, then four FFMA2 per output
+        // that also recombine the hi and lo tap parts:  z = (re_hi + j im_hi) a rot + (re_lo + j im_lo) b rot
+        const int quad = warp & 3, i = lane >> 2, j = lane & 3;
         const unsigned long long row_dph = (unsigned long long)S::ROW_S * p.step_fx;
-        const unsigned long long out_dph = (unsigned long long)D * p.step_fx;
         const unsigned long long tile_dph = (unsigned long long)S::TILE_S * p.step_fx;
-        const unsigned long long row_ph = p.phase0_fx + (unsigned long long)row * row_dph;
-        constexpr int RC = R < 4 ? R : 4;           // outputs per 16-column piece
-        // NCO: one polynomial rotation per piece (64-bit fixed-point phase of its first output), outputs 1 .. 3 of the piece by
-        // the angle-addition step e^{-j 2 pi r D step} (three constants per thread): one extra rounding, 14 instead of 45
-        // instructions per output
-        float2 rstep[RC > 1 ? RC - 1 : 1];
+        const int row0 = quad * 32 + i;
+        const unsigned long long row_ph = p.phase0_fx + (unsigned long long)row0 * row_dph;
+        float2 cstep[3];
 #pragma unroll
-        for (int r = 1; r < RC; ++r) rstep[r - 1] = nco_rot((unsigned long long)r * out_dph);
+        for (int h = 1; h < 4; ++h) cstep[h - 1] = nco_rot((unsigned long long)(8 * h) * row_dph);
+        constexpr int NB = R >= 8 ? R / 8 : 1;      // 32-column blocks (one 16-column block when R = 4)
+        constexpr int OB = R >= 8 ? 8 : 4;          // outputs of a row per block
         int acc = 0;
         uint32_t fpar = 0;
         for (int k = 0; k < n_k; ++k) {
             const long long t0 = p.dbg ? clock64() : 0;
-            mbar_wait_uni(&acc_full[acc], fpar);
+            TC_WAIT_SLACK(&acc_full[acc], fpar);
+            if (p.dbg) tw0 += clock64() - t0;
+            tc_fence_after();
+            const float2 rot0 = nco_rot_bf(row_ph + (unsigned long long)cc * tile_dph);
+            float2* o = p.out + (long long)cs * p.out_stride + (long long)cc * TILE_OUT;
+            const long long n_left = p.n_out - (long long)cc * TILE_OUT;   // outputs of this stream from the tile start on
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+                for (int blk = 0; blk < NB; ++blk) {
+                    uint32_t v[16];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32 + 16 * hf) << 16) + (uint32_t)(acc * N + 32 * blk);
+                    if (R >= 8) tc_ld_16x256_x4(taddr, v);
+                    else tc_ld_16x256_x2(taddr, v);
+                    tc_wait_ld();
+                    if (hf == 1 && blk == NB - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[acc]);   // accumulator back to the MMA warp
+                    }
+                    if ((p.debug_mode & 255) == 3) continue;   // debug_mode 3: no epilogue arithmetic or stores (tuning ceiling)
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int h = 2 * hf + hh;
+                        const float2 rot = h == 0 ? rot0 : cmul(rot0, cstep[h > 0 ? h - 1 : 0]);
+                        const float2 t_hi_re = make_float2(rot.x * tc.inv_scale, rot.y * tc.inv_scale);     // times a real part
+                        const float2 t_hi_im = make_float2(-t_hi_re.y, t_hi_re.x);                          // times an imaginary part
+                        const float2 t_lo_re = make_float2(rot.x * tc.lo_scale, rot.y * tc.lo_scale);
+                        const float2 t_lo_im = make_float2(-t_lo_re.y, t_lo_re.x);
+                        constexpr int NO = R >= 8 ? 2 : 1;   // outputs of this lane in the block
+                        float2 z[NO];
+#pragma unroll
+                        for (int oo = 0; oo < NO; ++oo) {
+                            const float re_hi = __uint_as_float(v[8 * oo + 2 * hh]), re_lo = __uint_as_float(v[8 * oo + 2 * hh + 1]);
+                            const float im_hi = __uint_as_float(v[8 * oo + 4 + 2 * hh]), im_lo = __uint_as_float(v[8 * oo + 4 + 2 * hh + 1]);
+                            float2 zz = make_float2(re_lo * t_lo_re.x, re_lo * t_lo_re.y);
+                            zz = ffma2(im_lo, t_lo_im, zz);
+                            zz = ffma2(re_hi, t_hi_re, zz);
+                            z[oo] = ffma2(im_hi, t_hi_im, zz);
+                        }
+                        const long long m = (long long)(row0 + 8 * h) * R + OB * blk + NO * j;   // first output of this lane
+                        const long long l = (p.debug_mode & 255) == 4 ? (long long)(z[0].x == 1.2345f) : n_left - m;   // debug_mode 4: (almost) no stores
+                        if (NO == 2 && p.vec_store) {
+                            st_cs_v4_if(o + m, z[0].x, z[0].y, z[NO - 1].x, z[NO - 1].y, l >= 2);
+                            st_cs_v2_if(o + m, z[0].x, z[0].y, l == 1);
+                        } else {
+#pragma unroll
+                            for (int oo = 0; oo < NO; ++oo) st_cs_v2_if(o + m + oo, z[oo].x, z[oo].y, l >= oo + 1);
+                        }
+                    }
+                }
+            }
+            acc ^= 1;
+            if (acc == 0) fpar ^= 1u;
+            cs += gs;
+            cc += gc;
+            if (cc >= cps) { cc -= cps; ++cs; }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ------------------------------------------------------------------ epilogue warps (fewer than four outputs per row):
+        // one row per lane, TMEM lanes 32 (warp % 4) ..
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+        const unsigned long long row_dph = (unsigned long long)S::ROW_S * p.step_fx;
+        const unsigned long long tile_dph = (unsigned long long)S::TILE_S * p.step_fx;
+        const unsigned long long row_ph = p.phase0_fx + (unsigned long long)row * row_dph;
+        constexpr int RC = R < 4 ? R : 4;           // outputs per 16-column piece
+        // NCO: the tap matrix carries the rotation by the sample's position INSIDE the row (k_tc.cu: build_b), so every output
+        // of a row takes the same residual rotation e^{-j 2 pi step (first sample of the row)}: one polynomial rotation (64-bit
+        // fixed-point phase) per row and tile, then four FFMA2 per output that also recombine the hi and lo tap parts:
+        //      z = (re_hi + j im_hi) a rot + (re_lo + j im_lo) b rot,      a = 512 / S, b = a 2^-11
+        int acc = 0;
+        uint32_t fpar = 0;
+        for (int k = 0; k < n_k; ++k) {
+            const long long t0 = p.dbg ? clock64() : 0;
+            TC_WAIT_SLACK(&acc_full[acc], fpar);
             if (p.dbg) tw0 += clock64() - t0;
             tc_fence_after();
             const long long m_row = (long long)cc * TILE_OUT + (long long)row * R;
             float2* o = p.out + (long long)cs * p.out_stride + m_row;
             const long long left = p.n_out - m_row;     // outputs of this row that exist (ragged stream tail)
-            unsigned long long ph = row_ph + (unsigned long long)cc * tile_dph;
+            const float2 rot = nco_rot_bf(row_ph + (unsigned long long)cc * tile_dph);
+            const float2 t_hi_re = make_float2(rot.x * tc.inv_scale, rot.y * tc.inv_scale);     // times a real part
+            const float2 t_hi_im = make_float2(-t_hi_re.y, t_hi_re.x);                          // times an imaginary part
+            const float2 t_lo_re = make_float2(rot.x * tc.lo_scale, rot.y * tc.lo_scale);
+            const float2 t_lo_im = make_float2(-t_lo_re.y, t_lo_re.x);
             constexpr int NCH = (4 * R + 15) / 16;      // 16-column pieces that hold outputs
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
@@ -289,17 +452,16 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[acc]);   // accumulator back to the MMA warp
                 }
-                const float2 rot0 = nco_rot_bf(ph);
-                ph += (unsigned long long)RC * out_dph;
+                if ((p.debug_mode & 255) == 3) continue;   // debug_mode 3: no epilogue arithmetic or stores (tuning ceiling)
                 float2 z[RC];
 #pragma unroll
                 for (int r = 0; r < RC; ++r) {
-                    const float yre = fmaf(__uint_as_float(v[4 * r + 1]), tc.lo_scale, __uint_as_float(v[4 * r + 0]) * tc.inv_scale);
-                    const float yim = fmaf(__uint_as_float(v[4 * r + 3]), tc.lo_scale, __uint_as_float(v[4 * r + 2]) * tc.inv_scale);
-                    const float2 y = r == 0 ? make_float2(yre, yim) : cmul(make_float2(yre, yim), rstep[r > 0 ? r - 1 : 0]);
-                    z[r] = cmul(y, rot0);
+                    float2 zz = make_float2(__uint_as_float(v[4 * r + 1]) * t_lo_re.x, __uint_as_float(v[4 * r + 1]) * t_lo_re.y);
+                    zz = ffma2(__uint_as_float(v[4 * r + 3]), t_lo_im, zz);
+                    zz = ffma2(__uint_as_float(v[4 * r + 0]), t_hi_re, zz);
+                    z[r] = ffma2(__uint_as_float(v[4 * r + 2]), t_hi_im, zz);
                 }
-                const long long l = left - ch * 4;
+                const long long l = (p.debug_mode & 255) == 4 ? (long long)(z[0].x == 1.2345f) : left - ch * 4;   // debug_mode 4: (almost) no stores
                 float2* oc = o + ch * 4;
                 if (RC >= 2 && p.vec_store) {
 #pragma unroll
@@ -321,71 +483,79 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
     } else if (warp >= 8) {
         // ------------------------------------------------------------------ unpack warps: all of them share every tile
         const int u = warp - 8;
-        const __half2 bias = __floats2half2_rn(1536.f, 1536.f);
-        uint32_t mulk[4] = {1u << 10, 1u << 14, 1u << 18, 1u << 22};
-        unsigned long long addend = 0x6400640000000000ull;
-        asm volatile("" : "+r"(mulk[0]), "+r"(mulk[1]), "+r"(mulk[2]), "+r"(mulk[3]), "+l"(addend));
         // lane -> 16-sample group inside a run of 32 groups.  A quarter warp's two STS.128 must hit eight distinct 16-byte bank
         // groups: four even sub-streams of one row and the same four of the next (sub-stream pitch = odd number of units), so
         // lane bit 2 selects the row (group bit LOG_NS - 1) and the other lane bits fill the remaining group bits in order.
         constexpr int HB = S::LOG_NS - 1;   // log2(groups per row)
         const int low = lane & 3, rsel = (lane >> 2) & 1, rest = lane >> 3;   // 2 + 1 + 2 bits
         const int gl = low | ((rest & ((1 << (HB - 2)) - 1)) << 2) | (rsel << HB) | ((rest >> (HB - 2)) << (HB + 1));
+        constexpr int UB = S::UNP_BATCH;    // groups a lane has in flight: all loads first, then the integer work, then the stores
+        // a lane's groups are GSTEP apart, so both its raw address (20 bytes per group) and its destination (2 * GSTEP units on =
+        // the same sub-stream, 2 * GSTEP / NS rows down) advance by compile-time constants
+        constexpr int GSTEP = 32 * NU, LD_STEP = 20 * GSTEP, ST_STEP = 2 * GSTEP / NS * 16;
+        static_assert((2 * GSTEP) % NS == 0, "a lane must stay on one sub-stream pair");
+        const int gfirst = u * 32 + gl;
+        const uint32_t ld_off = 20u * (uint32_t)gfirst;
+        const uint32_t st_off = (uint32_t)((2 * gfirst) & (NS - 1)) * (uint32_t)tc.a_pitch + (uint32_t)((2 * gfirst) >> S::LOG_NS) * 16u;
+        // One batch covers a lane's share of a tile (the launcher guarantees n_groups <= UB * GSTEP).  The raw words of tile
+        // k + 1 are loaded BEFORE the fence / arrive of tile k, so the shared-memory latency of the loads overlaps the drain of
+        // the stores and the integer work of a tile starts from registers; it also lets the twelve warps drift apart instead
+        // of running their load, ALU and store phases in lockstep.
+        const bool on = (p.debug_mode & 255) != 2;   // debug_mode 2: no unpack (tuning ceiling)
+        bool valid[UB];
+#pragma unroll
+        for (int b = 0; b < UB; ++b) valid[b] = on && gfirst + b * GSTEP < tc.n_groups;
+        uint32_t rw[UB][5];
+        auto load_raw = [&](int slot) {
+            const unsigned char* rp = rsm + (size_t)slot * tc.raw_slot_bytes + ld_off;
+#pragma unroll
+            for (int b = 0; b < UB; ++b) {
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(rp + b * LD_STEP);
+#pragma unroll
+                for (int i = 0; i < 5; ++i) rw[b][i] = valid[b] ? src[i] : 0u;
+            }
+        };
         int rs = 0, as = 0;
         uint32_t rpar = 0, epar = 1;
+        if (n_k > 0) {
+            mbar_wait_uni(&raw_full[0], 0);
+            load_raw(0);
+        }
         for (int k = 0; k < n_k; ++k) {
             const long long t0 = p.dbg ? clock64() : 0;
-            mbar_wait_uni(&raw_full[rs], rpar);
-            const long long t1 = p.dbg ? clock64() : 0;
             mbar_wait_uni(&a_empty[as], epar);
             const long long t2 = p.dbg ? clock64() : 0;
             if (p.dbg) tw0 += t2 - t0;
-            const unsigned char* raw = rsm + (size_t)rs * tc.raw_slot_bytes;
-            unsigned char* ast = asm_ + (size_t)as * tc.a_stage_bytes;
-            const int g_end = (p.debug_mode & 255) == 2 ? 0 : tc.n_groups;   // debug_mode 2: no unpack (tuning ceiling)
-#pragma unroll 2
-            for (int g = u * 32 + gl; g < g_end; g += 32 * NU) {
-                // 16 samples = 160 bits, big-endian bit stream: sample s = bits [10 s, 10 s + 10) from the top
-                const uint32_t* rw = reinterpret_cast<const uint32_t*>(raw + 20 * g);
-                uint32_t be[5];
+            unsigned char* sp = asm_ + (size_t)as * tc.a_stage_bytes + st_off;
 #pragma unroll
-                for (int i = 0; i < 5; ++i) be[i] = __byte_perm((p.debug_mode & 0x20) ? (uint32_t)g * 2654435761u + i : rw[i], 0, 0x0123);
+            for (int b = 0; b < UB; ++b) {
                 uint32_t h[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    // pair q = samples 2q, 2q+1 = 20 bits from bit 20 q of the group.  One LOP3 flips the two sign bits (offset
-                    // binary u = v + 512) and isolates the pair; one 32 x 32 -> 64 bit multiply-add by a power of two then leaves
-                    // u_a (+ the exponent pattern of 1024.0 for both halves) in the high word and u_b in the top ten bits of the
-                    // low word; one shift-add drops u_b into the high half: 0x6400 | u in each half = 1024 + u, minus 1536 = v.
-                    // (4 instructions per pair, 2 on the ALU pipe and 2 on the FMA pipe; pairs that straddle two words take a
-                    // funnel shift first.)
-                    const int bit = 20 * q, wi = bit >> 5, sh = bit & 31;
-                    const bool straddle = sh + 20 > 32;
-                    const uint32_t src = straddle ? __funnelshift_l(be[wi + 1 > 4 ? 4 : wi + 1], be[wi], sh) : be[wi];
-                    const int s2 = straddle ? 0 : sh;
-                    uint32_t fm;
-                    asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(fm) : "r"(src), "r"(0x80200000u >> s2), "r"(0xFFFFF000u >> s2));   // (src ^ x) & m
-                    uint32_t plo, phi;   // IMAD.WIDE with the 64-bit addend; the multipliers sit in registers so that ptxas keeps the multiply
-                    asm("{\n.reg .b64 t;\nmad.wide.u32 t, %2, %3, %4;\nmov.b64 {%0, %1}, t;\n}" : "=r"(plo), "=r"(phi) : "r"(fm), "r"(mulk[s2 >> 2]), "l"(addend));
-                    const uint32_t w = phi + (plo >> 6);
-                    const __half2 hv = __hsub2(*reinterpret_cast<const __half2*>(&w), bias);   // exact
-                    h[q] = *reinterpret_cast<const uint32_t*>(&hv);
-                }
+                tc_unpack16(rw[b], h, tc);
                 // units 2g (even sub-stream) and 2g + 1 (the next sub-stream, same row)
-                unsigned char* dst = ast + (size_t)((2 * g) & (NS - 1)) * tc.a_pitch + (size_t)((2 * g) >> S::LOG_NS) * 16;
-                if (!(p.debug_mode & 0x10) || (h[0] ^ h[5]) == 0x12345678u) {   // debug bit 0x10: no stores (tuning)
+                unsigned char* dst = sp + b * ST_STEP;
+                if (valid[b]) {
                     *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
                     *reinterpret_cast<uint4*>(dst + tc.a_pitch) = make_uint4(h[4], h[5], h[6], h[7]);
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&raw_empty[rs]);   // every lane's raw words have been consumed
+            if (++rs == tc.n_raw) { rs = 0; rpar ^= 1u; }
             if (p.dbg) tw1 += clock64() - t2;
+            // next tile's raw words: now if they have landed (the usual case: the producer runs slots ahead), else after the
+            // hand-over of this stage, so that a late copy never delays the MMA of the tile just unpacked
+            const bool more = k + 1 < n_k;
+            const bool early = more && mbar_test_uni(&raw_full[rs], rpar);
+            if (early) load_raw(rs);
             fence_proxy_async();   // my stores before the tensor core's reads of this stage
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&a_full[as]);
-                mbar_arrive(&raw_empty[rs]);
+            if (lane == 0) mbar_arrive(&a_full[as]);
+            if (more && !early) {
+                const long long t3 = p.dbg ? clock64() : 0;
+                mbar_wait_uni(&raw_full[rs], rpar);
+                if (p.dbg) tw0 += clock64() - t3;
+                load_raw(rs);
             }
-            if (++rs == tc.n_raw) { rs = 0; rpar ^= 1u; }
             if (++as == tc.n_a) { as = 0; epar ^= 1u; }
         }
     }

@@ -998,6 +998,11 @@ int ddcb200_set_option(ddcb200_t* h, const char* key, int64_t value) {
         h->tc_ns = (int)value;
         return DDCB200_OK;
     }
+    if (!strcmp(key, "tc_na") || !strcmp(key, "tc_nraw")) {   // tuning: pipeline depths of the tensor engine (0 = automatic)
+        if (value < 0 || value > 8) return fail(DDCB200_EINVAL, "%s must be 0 .. 8", key);
+        (key[4] == 'a' ? h->tc_na : h->tc_nraw) = (int)value;
+        return DDCB200_OK;
+    }
     if (!strcmp(key, "l2_ahead")) {
         h->l2_ahead = (int)value;
         return DDCB200_OK;

@@ -23,7 +23,7 @@ struct TcGeom {
 };
 
 // geometry of one (T, D, NS): NS sub-streams = MMA rows of 8 NS samples = R = 8 NS / D outputs, N = 4 R accumulator columns
-TcGeom tc_geometry(int T, int D, int NS) {
+TcGeom tc_geometry(int T, int D, int NS, int force_na = 0, int force_nraw = 0) {
     TcGeom g{};
     g.D = D;
     g.T = T;
@@ -43,12 +43,21 @@ TcGeom tc_geometry(int T, int D, int NS) {
     g.b_bytes = g.N * g.K * 2;
     g.ok = false;
     if (g.R < 1 || g.N > 256) return g;
+    if (g.n_groups > TcShape<8>::UNP_BATCH * 32 * TcShape<8>::NUNP) return g;   // one unpack batch per lane and tile
     const size_t cap = 227 * 1024;
-    for (int n = 4; n >= 2 && !g.ok; --n) {
-        g.n_a = n;
-        g.n_raw = n;
-        g.smem = 1024 + (size_t)((g.b_bytes + 127) & ~127) + (size_t)n * g.a_stage + (size_t)n * g.raw_slot;
-        g.ok = g.smem <= cap;
+    const size_t fixed = 1024 + (size_t)((g.b_bytes + 127) & ~127);
+    // two A stages are enough for the MMA of one tile to overlap the unpack of the next (three when memory allows); everything
+    // else goes to the raw ring: packed bytes in flight are what hides the HBM latency (up to 8 slots, the barrier arrays' size)
+    for (int na = (force_na ? force_na : 3); na >= 2 && !g.ok; --na) {
+        if (fixed + (size_t)na * g.a_stage + 2 * (size_t)g.raw_slot > cap) { if (force_na) break; continue; }
+        int nr = (int)((cap - fixed - (size_t)na * g.a_stage) / (size_t)g.raw_slot);
+        nr = std::min(nr, 8);
+        if (force_nraw) nr = std::min(nr, force_nraw);
+        if (na == 3 && nr < 4 && !force_na) continue;   // prefer a deeper raw ring over the third A stage
+        g.n_a = na;
+        g.n_raw = nr;
+        g.smem = fixed + (size_t)na * g.a_stage + (size_t)nr * g.raw_slot;
+        g.ok = nr >= 2;
     }
     // descriptor fields are 14 bits of 16-byte units (the sums the MMA warp forms must not carry out of the address field)
     if (g.smem / 16 >= (1u << 14) || g.a_pitch / 16 >= (1 << 13)) g.ok = false;
@@ -57,37 +66,38 @@ TcGeom tc_geometry(int T, int D, int NS) {
 
 // sub-stream count for a (T, D): option "tc_ns" forces one; otherwise the widest rows that leave three pipeline stages
 TcGeom tc_pick(const ddcb200* h, int T, int D) {
-    if (h && h->tc_ns) return tc_geometry(T, D, h->tc_ns);
+    if (h && (h->tc_ns || h->tc_na || h->tc_nraw)) return tc_geometry(T, D, h->tc_ns ? h->tc_ns : 16, h->tc_na, h->tc_nraw);
     TcGeom best{};
-    for (int ns : {8}) {
+    for (int ns : {16, 8}) {   // 128-sample rows halve the operand re-reads of 64-sample rows; the latter fit longer filters
+        if (ns == 16 && D < 8) continue;
         const TcGeom g = tc_geometry(T, D, ns);
-        if (g.ok && (!best.ok || g.n_a >= 3)) best = g;
+        if (g.ok && !best.ok) best = g;
     }
     return best;
 }
 
-// B[(r, c), k] = part c of S * tap(k - D r): c = 0 re_hi, 1 re_lo * 2^11, 2 im_hi, 3 im_lo * 2^11; image [K / 8][N][8] halves
+// B[(r, c), k] = part c of S * tap(k - D r) * e^{-j 2 pi step k}: c = 0 re_hi, 1 re_lo * 2^11, 2 im_hi, 3 im_lo * 2^11; image
+// [K / 8][N][8] halves.  The rotation goes by the sample's position k inside the ROW, not inside the tap window, so that all
+// the outputs of a row are left with one common rotation for the epilogue.
 void build_b(const ddcb200* h, double step, const TcGeom& g, __half* out, float* inv_scale, float* lo_scale) {
     const int T = g.T;
-    std::vector<double> cre(T), cim(T);
+    std::vector<double> rc(g.K), rs(g.K);
     const double fstep = step - std::floor(step);
-    double amax = 0.0;
-    for (int k = 0; k < T; ++k) {
-        const double hk = h->taps[T - 1 - k] / h->taps_sum;
+    for (int k = 0; k < g.K; ++k) {
         double ph = fstep * (double)k;
         ph -= std::floor(ph);
-        const double a = -2.0 * M_PI * ph;
-        cre[k] = hk * std::cos(a);
-        cim[k] = hk * std::sin(a);
-        amax = std::max(amax, std::max(std::fabs(cre[k]), std::fabs(cim[k])));
+        rc[k] = std::cos(-2.0 * M_PI * ph);
+        rs[k] = std::sin(-2.0 * M_PI * ph);
     }
+    double hmax = 0.0;
+    for (int t = 0; t < T; ++t) hmax = std::max(hmax, std::fabs(h->taps[t] / h->taps_sum));
     int e = 0;
-    if (amax > 0.0) e = (int)std::floor(std::log2(32768.0 / amax));
-    if (std::ldexp(amax, e) >= 32768.0) --e;
+    if (hmax > 0.0) e = (int)std::floor(std::log2(32768.0 / hmax));
+    if (std::ldexp(hmax, e) >= 32768.0) --e;
     e = std::max(-14, std::min(e, 40));
     const double S = std::ldexp(1.0, e);
-    *inv_scale = (float)(1.0 / S);
-    *lo_scale = (float)(1.0 / (2048.0 * S));
+    *inv_scale = (float)(512.0 / S);             // the kernel's unpack delivers v / 512
+    *lo_scale = (float)(512.0 / (2048.0 * S));
     std::memset(out, 0, (size_t)g.b_bytes);
     auto split = [&](double v, __half& hi, __half& lo) {
         hi = __float2half_rn((float)(v * S));
@@ -97,14 +107,15 @@ void build_b(const ddcb200* h, double step, const TcGeom& g, __half* out, float*
     for (int r = 0; r < g.R; ++r)
         for (int t = 0; t < T; ++t) {
             const int k = t + g.D * r;
+            const double hk = h->taps[T - 1 - t] / h->taps_sum;
             __half* col = out + ((size_t)(k / 8) * g.N) * 8 + (k % 8);
             __half hi, lo;
-            split(cre[t], hi, lo);
-            col[(size_t)(4 * r + 0) * 8] = hi;
-            col[(size_t)(4 * r + 1) * 8] = lo;
-            split(cim[t], hi, lo);
-            col[(size_t)(4 * r + 2) * 8] = hi;
-            col[(size_t)(4 * r + 3) * 8] = lo;
+            split(hk * rc[k], hi, lo);
+            col[(size_t)tc_col(g.R, r, 0) * 8] = hi;
+            col[(size_t)tc_col(g.R, r, 1) * 8] = lo;
+            split(hk * rs[k], hi, lo);
+            col[(size_t)tc_col(g.R, r, 2) * 8] = hi;
+            col[(size_t)tc_col(g.R, r, 3) * 8] = lo;
         }
 }
 
@@ -192,6 +203,8 @@ int launch_tc10(ddcb200* h, RunParams& p, cudaStream_t st, double step, int D) {
     tc.n_raw = g.n_raw;
     tc.inv_scale = h->tc_inv_scale;
     tc.lo_scale = h->tc_lo_scale;
+    tc.unp_mul[0] = 1u << 10;
+    tc.unp_mul[1] = 1u << 14;
 
     const long long tile_out = 128LL * g.R;
     p.tiles_per_stream = (p.n_out + tile_out - 1) / tile_out;
