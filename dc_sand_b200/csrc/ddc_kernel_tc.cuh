@@ -1,30 +1,37 @@
-// Tensor-core engine for PACKED 10-bit input ("kernel TC", opt-in: option "variant" = 13 / engine="tensor").
+// Tensor-core engine for PACKED 10-bit input ("kernel TC"): the default for packed input (option "packed_engine" = 1; 0 keeps
+// the CUDA-core kernels of ddc_kernel_w10.cuh / _p.cuh; option "variant" = 13 forces this engine).
 //
 // Why it exists: packed input is FP32-bound by 3.2x on the CUDA cores (1.75 B against 64 flop per sample at T = 256, D = 16), so
 // the fused-unpack fast-FIR kernel sits at 26 % of the HBM roofline however well it is scheduled.  10-bit samples are EXACT in
 // fp16, and a decimating FIR over a tile of outputs is a Toeplitz product, so for this input type -- and only for it -- the
 // filter can run on tcgen05 without giving up the reference's precision: taps are split hi + lo into two fp16 values
 // (22 significant bits, the float32 taps of the CUDA-core kernels have 24), products are exact, accumulation is FP32 in TMEM.
-// The float32-input kernels stay on the CUDA cores (north star): a float32 sample is not exact in any tensor-core input type.
+// Measured against the float64 oracle it is as close as the CUDA-core kernels (max error 7e-7 of full scale at T = 256, 2e-6
+// at T = 1024; tests/test_gpu_tensor_engine.py).  The float32-input kernels stay on the CUDA cores (north star): a float32
+// sample is not exact in any tensor-core input type.
 //
-// Formulation.  One MMA row covers 64 consecutive input samples = R = 64 / D outputs:
-//      Y[row, (r, c)] = sum_k  X[row, k] * B[(r, c), k],     X[row, k] = x[64 row + k],   k = 0 .. K-1,  K = 64 - D + T (padded to 16)
-//      B[(r, c), k]   = part c of tap  k - D r               (c: re_hi, re_lo, im_hi, im_lo;  0 outside [0, T))
-// i.e. M = 128 rows (8192 samples) x N = 4 R columns x K per tile; the structured zeros of B cost (R - 1) D / T extra MACs
-// (19 % at T = 256, D = 16) and make N a legal tcgen05 shape.  X is never materialised: the unpack warps write the fp16 sample
-// stream into shared memory as EIGHT SUB-STREAMS of 16-byte units (unit u = samples 8u .. 8u+7 goes to sub-stream u % 8, row
-// u / 8), and because consecutive rows of X start exactly one row further on in every sub-stream, the canonical no-swizzle
-// K-major operand layout of tcgen05 (8-row core matrices of 16-byte rows, SBO = 128 bytes between row groups, LBO = the
-// distance between two sub-streams for the two K-units of one MMA) describes the overlapping windows directly: K-unit q of
-// row m is unit 8 m + q = sub-stream q % 8, row m + q / 8.  An MMA for K-units (2i, 2i+1) just starts (2i) / 8 rows down
-// sub-stream (2i) % 8.
+// Formulation.  One MMA row covers ROW_S = 8 NS consecutive input samples (NS = 16: 128 samples) = R = ROW_S / D outputs:
+//      Y[row, (r, c)] = sum_k  X[row, k] * B[(r, c), k],     X[row, k] = x[ROW_S row + k],   k = 0 .. K-1,  K = ROW_S - D + T (padded to 16)
+//      B[(r, c), k]   = part c of  tap(k - D r) e^{-j 2 pi step k}     (c: re_hi, re_lo, im_hi, im_lo;  0 outside the tap window)
+// i.e. M = 128 rows x N = 4 R columns x K per tile; the structured zeros of B cost (R - 1) D / T extra MACs and make N a legal
+// tcgen05 shape.  The NCO rotation inside B goes by the sample's position in the ROW, which leaves every output of a row
+// with the same residual rotation for the epilogue.  X is never materialised: the unpack warps write the fp16 sample stream
+// into shared memory as NS SUB-STREAMS of 16-byte units (unit u = samples 8u .. 8u+7 goes to sub-stream u % NS, row u / NS),
+// and because consecutive rows of X start exactly one row further on in every sub-stream, the canonical no-swizzle K-major
+// operand layout of tcgen05 (8-row core matrices of 16-byte rows, SBO = 128 bytes between row groups, LBO = the distance
+// between two sub-streams for the two K-units of one MMA) describes the overlapping windows directly: K-unit q of row m is
+// unit NS m + q = sub-stream q % NS, row m + q / NS.  An MMA for K-units (2i, 2i+1) just starts (2i) / NS rows down
+// sub-stream (2i) % NS.
 //
-// Pipeline per CTA (one per SM, persistent, 16 warps):
-//      warp 0      TMA producer: one bulk copy of packed bytes per tile -> raw ring
-//      warps 8-15  unpack: 20 bytes -> 16 fp16 per lane and step (integer work, bit-exact), two STS.128 into the sub-streams
+// Pipeline per CTA (one per SM, persistent, 8 + NUNP warps):
+//      warp 0      TMA producer: one bulk copy of packed bytes per tile -> raw ring (up to 8 slots: HBM latency)
+//      warps 8..   unpack: 20 bytes -> 16 fp16 per lane and group, bit-exact (PRMT, LOP3, IMAD.WIDE, LEA.HI, HFMA2 per sample
+//                  pair), raw words of the NEXT tile already in registers, two STS.128 per group into the sub-streams
 //      warp 1      one elected thread issues K / 16 tcgen05.mma per tile into one of two TMEM accumulators
-//      warps 4-7   epilogue: tcgen05.ld, hi + lo recombination, NCO rotation (64-bit fixed-point phase), streaming stores
-// SASS evidence: UBLKCP, UTCHMMA, LDTM (profiles/r2_sass_mnemonics.txt).
+//      warps 4-7   epilogue: tcgen05.ld in the 16x256b fragment layout (a quad of lanes holds one row's outputs, so the warp's
+//                  stores cover whole sectors), hi + lo recombination and NCO rotation in four FFMA2 per output, streaming stores
+// Shared-memory bandwidth bounds it (operand re-reads of the MMA: (128 + N) * 32 B per K-step, + unpack traffic), not the
+// tensor pipe and not the CUDA cores: DESIGN.md section 4.7.  SASS evidence: UBLKCP, UTCHMMA, LDTM (profiles/r2_sass_mnemonics.txt).
 #pragma once
 #include <cuda_fp16.h>
 
@@ -36,34 +43,8 @@
 #ifndef DDCB200_TC_UB
 #define DDCB200_TC_UB 3
 #endif
-#ifndef DDCB200_TC_SLEEP_NS
-#define DDCB200_TC_SLEEP_NS 0
-#endif
 
 namespace ddck {
-
-// wait of a warp with slack in its schedule (producer, epilogue): back off between polls so that the spin does not take issue
-// slots and shared-memory transactions from the unpack warps
-__device__ __forceinline__ void mbar_wait_uni_sleep(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p, q;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "vote.sync.all.pred q, p, 0xffffffff;\n"
-        "@q bra.uni DONE_%=;\n"
-        "nanosleep.u32 %2;\n"
-        "bra.uni WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity), "r"(DDCB200_TC_SLEEP_NS)
-        : "memory");
-}
-#if DDCB200_TC_SLEEP_NS > 0
-#define TC_WAIT_SLACK(bar, par) mbar_wait_uni_sleep(bar, par)
-#else
-#define TC_WAIT_SLACK(bar, par) mbar_wait_uni(bar, par)
-#endif
 
 struct TcParams {
     const void* b_mat;        // fp16 B operand in its shared-memory image: [K / 8][N][8] halves
@@ -266,7 +247,7 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
         uint32_t par = 1;   // first pass: the slots are free
         for (int k = 0; k < n_k; ++k) {
             const long long t0 = p.dbg ? clock64() : 0;
-            TC_WAIT_SLACK(&raw_empty[slot], par);
+            mbar_wait_uni(&raw_empty[slot], par);
             if (p.dbg) tw0 += clock64() - t0;
             const unsigned char* src = reinterpret_cast<const unsigned char*>(p.in) + (long long)cs * p.in_stride + (long long)cc * S::TILE_PACKED;
             unsigned char* dst = rsm + (size_t)slot * tc.raw_slot_bytes;
@@ -355,7 +336,7 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
         uint32_t fpar = 0;
         for (int k = 0; k < n_k; ++k) {
             const long long t0 = p.dbg ? clock64() : 0;
-            TC_WAIT_SLACK(&acc_full[acc], fpar);
+            mbar_wait_uni(&acc_full[acc], fpar);
             if (p.dbg) tw0 += clock64() - t0;
             tc_fence_after();
             const float2 rot0 = nco_rot_bf(row_ph + (unsigned long long)cc * tile_dph);
@@ -430,7 +411,7 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
         uint32_t fpar = 0;
         for (int k = 0; k < n_k; ++k) {
             const long long t0 = p.dbg ? clock64() : 0;
-            TC_WAIT_SLACK(&acc_full[acc], fpar);
+            mbar_wait_uni(&acc_full[acc], fpar);
             if (p.dbg) tw0 += clock64() - t0;
             tc_fence_after();
             const long long m_row = (long long)cc * TILE_OUT + (long long)row * R;

@@ -282,7 +282,8 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         p.m_begin = 0;
     };
 
-    // ---- packed 10-bit input on the tensor cores (opt-in: option "packed_engine" = 1 or "variant" = 13; ddc_kernel_tc.cuh) ---
+    // ---- packed 10-bit input on the tensor cores (default engine for packed input; option "packed_engine" = 0 or a CUDA-core
+    // "variant" selects the kernels below; "variant" = 13 forces it; ddc_kernel_tc.cuh) ---
     if (packed && (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (in_stride % 16 == 0) && pow2_d &&
         (fv == 13 || (fv == 0 && h->packed_engine == 1)) && ddch::tc10_supported(h, T, D) &&
         (double)((M + 127) / 128) * (double)n_streams < 2.0e9)
@@ -988,7 +989,7 @@ int ddcb200_set_option(ddcb200_t* h, const char* key, int64_t value) {
         }
         return DDCB200_OK;
     }
-    if (!strcmp(key, "packed_engine")) {   // 0: CUDA cores (default); 1: tcgen05 tensor cores for packed 10-bit input
+    if (!strcmp(key, "packed_engine")) {   // 1: tcgen05 tensor cores for packed 10-bit input (default); 0: CUDA cores
         if (value != 0 && value != 1) return fail(DDCB200_EINVAL, "packed_engine must be 0 or 1");
         h->packed_engine = (int)value;
         return DDCB200_OK;

@@ -187,6 +187,10 @@ const char* ddcb200_last_variant(ddcb200_t* handle);
  *   "chunk_samples"  time-chunk size of the host path (default 2^24 samples per launch);
  *   "copy_threads"   host threads that stage pageable input through pinned buffers and widen complex128 output (default 4,
  *                    0 = leave pageable copies to the driver);
+ *   "packed_engine"  engine for packed 10-bit input: 1 (default) the tcgen05 tensor-core engine wherever it applies
+ *                    (decimation 4 .. 64 a power of two, 16-byte aligned rows, filter fits shared memory), 0 the CUDA-core
+ *                    kernels; float32 input always runs on the CUDA cores;
+ *   "tc_ns", "tc_na", "tc_nraw"   tuning of the tensor engine (row width, A stages, raw slots; 0 = automatic);
  *   "debug_mode", "dbg_counters", "l2_ahead", "stagger_cycles"   measurement aids of the kernels (compute-only / memory-only
  *                    ceilings, ring wait-time counters). */
 int ddcb200_set_option(ddcb200_t* handle, const char* key, int64_t value);

@@ -251,7 +251,7 @@ def test_odd_row_pitch_and_offset_outputs(taps_dir, packed):
         flat = torch.zeros(3 * pitch + 4, dtype=torch.complex64, device="cuda")
         out = flat[off: off + 3 * pitch].view(3, pitch)[:, :m]
         ddc.run_tensor(x, 100e6, out=out, packed=packed)
-        assert "fast_fir" in ddc.last_variant, ddc.last_variant
+        assert ("tensor_fir" if packed else "fast_fir") in ddc.last_variant, ddc.last_variant
         emax, el2 = rel_err(out.cpu().numpy(), ref)
         assert emax <= TOL_MAX and el2 <= TOL_L2, (pitch, off, emax, el2)
         # nothing outside the M valid outputs of each row was written
@@ -555,18 +555,22 @@ def test_run_on_large_pageable_array(taps_dir):
     assert np.array_equal(ddc.run(x, 100e6), y)
 
 
+@pytest.mark.parametrize("engine", [0, 1])
 @pytest.mark.parametrize("d,t", [(16, 1024), (8, 256), (32, 512), (16, 40)])
-def test_packed_input_any_filter(d, t, tmp_path):
-    """Packed input for (T, D) without a fused-unpack kernel goes through the unpack stage into a workspace and then the
-    float32 kernel of that cell; same result as unpacking on the host first."""
+def test_packed_input_any_filter(d, t, engine, tmp_path):
+    """Packed input for any (T, D), both engines: on the CUDA cores a cell without a fused-unpack kernel goes through the
+    unpack stage into a workspace and then the float32 kernel of that cell; the tensor engine (default) covers them all
+    fused.  Same result as unpacking on the host first."""
     from scipy import signal
 
     n = 400_000
     tp = signal.firwin(t, 0.8 / d)
     xi = np.stack([synth.digitiser_stream(n, 40 + d + s) for s in range(2)])
     ddc = DigitalDownConverter(d, FS, _custom_taps(tmp_path, tp))
+    ddc.set_option("packed_engine", engine)
     yp = ddc.run_tensor(torch.from_numpy(np.stack([synth.pack10(r) for r in xi])).cuda(), 100e6, packed=True).cpu().numpy()
     variant = ddc.last_variant
+    assert ("tensor_fir" in variant) == bool(engine), variant
     yf = ddc.run_tensor(torch.from_numpy(xi.astype(np.float32)).cuda(), 100e6).cpu().numpy()
     assert "generic" not in variant, variant
     assert np.array_equal(yp, yf) or np.abs(yp - yf).max() <= TOL_MAX * np.abs(yf).max(), variant

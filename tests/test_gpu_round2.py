@@ -81,6 +81,7 @@ def test_fused_unpack_kernels_full_code_range(d, t, variant, name, bit_equal, tm
     tp = signal.firwin(t, 0.8 / d) if t != 256 or d != 16 else taps.coefficients("ddc_coeff_107MHz.csv")
     ddc = DigitalDownConverter(d, FS, _custom_taps(tmp_path, tp))
     ddc.set_option("variant", variant)
+    ddc.set_option("packed_engine", 0)   # the CUDA-core kernels (the tensor engine, default since round 2: test_gpu_tensor_engine.py)
     yp = ddc.run_tensor(torch.from_numpy(packed).cuda(), 100e6, packed=True)
     assert name in ddc.last_variant and "unpack10+" not in ddc.last_variant, ddc.last_variant
     ddc.set_option("variant", 0)
