@@ -276,7 +276,15 @@ def roofline_of(n_streams, n, m, t, d, packed, kern_s, variant, hbm_peak, peak_s
     b_in = 1.25 if packed else 4.0
     alg_bytes = n_streams * n * (b_in + 8.0 / d)
     flops = 4.0 * t * m * n_streams
-    exec_flops = flops * (0.75 if "fast_fir" in variant else 1.0)
+    tensor = variant.startswith("tensor_fir")   # packed input on tcgen05: no FIR flops on the CUDA cores at all
+    exec_flops = 0.0 if tensor else flops * (0.75 if "fast_fir" in variant else 1.0)
+    tensor_flops = None
+    if tensor:   # MACs the engine issues, zeros of the banded tap matrix included: 128 x N x K per tile of 128 rows
+        import re
+
+        g = {k: int(v) for k, v in re.findall(r"(ROW|N|K)(\d+)", variant)}
+        tiles = -(-m // (128 * (g["ROW"] // d))) * n_streams
+        tensor_flops = 2.0 * 128 * g["N"] * g["K"] * tiles
     t_hbm = alg_bytes / (hbm_peak * 1e9)
     t_fp32 = exec_flops / (FP32_PEAK_TFLOPS * 1e12)
     achieved = alg_bytes / kern_s / 1e9
@@ -299,6 +307,8 @@ def roofline_of(n_streams, n, m, t, d, packed, kern_s, variant, hbm_peak, peak_s
         "kernel_ms_mean": kern_s * 1e3,
         "algorithmic_bytes_per_launch": alg_bytes,
         "flop_per_launch_direct_form": flops,
+        "engine": "tcgen05 (fp16 samples x hi+lo fp16 taps, FP32 accumulate in TMEM)" if tensor else "CUDA cores (FP32 FFMA2)",
+        "tensor_tflops_issued": None if tensor_flops is None else tensor_flops / kern_s / 1e12,
     }
 
 
@@ -549,6 +559,11 @@ def run_extras(args, torch, dev, local, gen_input, time_device, parity_window, h
     ms3 = time_device(ddc, x3, y3, True, steps3, 3) / steps3
     v3 = ddc.last_variant
     err3 = parity_window(ddc, x3, y3, True, n3, T, D, seed=3)
+    ddc.set_option("packed_engine", 0)          # the same workload on the CUDA-core fused-unpack kernel, for comparison
+    ms3c = time_device(ddc, x3, y3, True, steps3, 3) / steps3
+    v3c = ddc.last_variant
+    err3c = parity_window(ddc, x3, y3, True, n3, T, D, seed=3)
+    ddc.set_option("packed_engine", 1)
     h_in = torch.empty(x3.shape, dtype=torch.uint8, pin_memory=True)
     h_in.copy_(x3)
     h_out = torch.empty((s3, m3), dtype=torch.complex64, pin_memory=True)
@@ -567,6 +582,9 @@ def run_extras(args, torch, dev, local, gen_input, time_device, parity_window, h
         "roofline": roofline_of(s3, n3, m3, T, D, True, ms3 * 1e-3, v3, hbm_peak, peak_src, ncu_traffic("c3", v3)),
         "e2e": {"value": s3 * n3 / e2e3 / 1e9, "unit": "Gsamples/s", "ms_per_step": e2e3 * 1e3,
                 "h2d_bytes_per_step": x3.numel(), "d2h_bytes_per_step": s3 * m3 * 8},
+        "cuda_cores": {"ms": ms3c, "gsamples_per_s": s3 * n3 / ms3c / 1e6, "kernel": v3c, "parity_max_err": err3c,
+                       "hbm_frac": roofline_of(s3, n3, m3, T, D, True, ms3c * 1e-3, v3c, hbm_peak, peak_src)["frac"],
+                       "note": "option packed_engine = 0: the round-1 fused-unpack kernel"},
     }
     del x3, y3, h_in, h_out
     ddc.close()
@@ -600,11 +618,17 @@ def run_extras(args, torch, dev, local, gen_input, time_device, parity_window, h
                             "bound": r["bound"], "hbm_frac": r["frac"], "fp32_executed_frac": r["fp32_executed_frac"],
                             "floor_frac": r["floor_frac"],
                             "parity_max_err": parity_window(c, xin, y4, pk, n4, t, d, seed=t + d)})
+                if pk:   # the same cell on the CUDA-core kernels (option packed_engine = 0)
+                    c.set_option("packed_engine", 0)
+                    msc = time_device(c, xin, y4, pk, 10, 3) / 10
+                    dst[-1].update({"ms_cuda_cores": msc, "kernel_cuda_cores": c.last_variant.split("<")[0]})
+                    c.set_option("packed_engine", 1)
             del y4
             c.close()
     extra["sweep"] = {"workload": "1 stream x 2^26 float32 samples, firwin(T, 0.8 / D) taps (the shipped 107 MHz filter at T = 256); "
                                   "3 warm-up + 10 launches per cell (BASELINE configs[3])", "cells": sweep}
-    extra["sweep_packed"] = {"workload": "the same cells on the packed 10-bit form of the same samples", "cells": sweep_packed}
+    extra["sweep_packed"] = {"workload": "the same cells on the packed 10-bit form of the same samples: default engine (tcgen05 tensor "
+                                         "cores, unpack fused in every cell) and, as ms_cuda_cores, the CUDA-core kernels", "cells": sweep_packed}
     del x4p
     torch.cuda.empty_cache()
 
