@@ -78,6 +78,7 @@ struct ddcb200 {
     float tc_inv_scale = 1.f, tc_lo_scale = 1.f;
     int tc_na = 0, tc_nraw = 0;            // options "tc_na" / "tc_nraw": force the A-stage / raw-slot counts (tuning)
     int tc_ns = 0, tc_ns_built = 0;        // option "tc_ns": force the sub-stream count (tuning); the one of the cached image
+    int host_chunk_mode = 0;               // option "host_chunk_mode": 0 by-stream chunks for batches of short streams, 1 time chunks
     int packed_engine = 1;                 // option "packed_engine": 1 tensor cores where supported (default), 0 CUDA cores
     ddcb200_c64* h_ostage[kBufs] = {};   // pinned landing buffers for the complex128 host path (one per chunk buffer)
     size_t ostage_cap = 0;

@@ -553,16 +553,23 @@ int run_host(ddcb200* h, const void* h_in, bool packed, int64_t n_samples, int64
     if (n_samples < T) return fail(DDCB200_ETOOSHORT, "n_samples (%lld) < n_taps (%d)", (long long)n_samples, T);
     if (packed && (n_samples % 4)) return fail(DDCB200_EINVAL, "packed input needs n_samples %% 4 == 0");
     const int64_t M = (n_samples - T) / D + 1;
-    // chunk length in outputs; inputs of a chunk start at a multiple of 4*D samples so that packed chunks start on a
-    // byte boundary and float chunks stay 16-byte aligned
+    // Chunking.  A batch whose whole streams fit the chunk budget is cut BY STREAM: a chunk is a group of whole rows, which for
+    // contiguous rows is one flat copy each way (no 2-D copy, no halo copied twice).  Longer streams are cut in TIME: chunk
+    // length in outputs, inputs of a chunk start at a multiple of 64 samples so that packed chunks start on a byte boundary and
+    // float chunks stay 16-byte aligned.  Option "host_chunk_mode" = 1 forces time chunks.
+    const bool by_stream = n_streams > 1 && !h_out128 && h->host_chunk_mode != 1 && n_samples <= h->chunk_samples;
+    const int64_t spc = by_stream ? std::max<int64_t>(1, std::min<int64_t>(h->chunk_samples / n_samples, (n_streams + 2) / 3))
+                                  : n_streams;                       // streams per chunk (at least three chunks: the pipeline)
+    const int64_t n_sgroups = (n_streams + spc - 1) / spc;
     int64_t per_stream = std::max<int64_t>(h->chunk_samples / n_streams, (int64_t)4 * T);
-    int64_t m_chunk = std::max<int64_t>(per_stream / D, 1);
+    int64_t m_chunk = by_stream ? M : std::max<int64_t>(per_stream / D, 1);
     m_chunk = ((m_chunk + 63) / 64) * 64;   // chunk starts stay 16-byte aligned for float32 AND packed (64 samples = 80 B)
-    const int64_t n_chunks = (M + m_chunk - 1) / m_chunk;
-    const int64_t in_chunk_samples = ((m_chunk - 1) * D + T + 63) / 64 * 64;
+    const int64_t n_tchunks = (M + m_chunk - 1) / m_chunk;
+    const int64_t n_chunks = n_tchunks * n_sgroups;
+    const int64_t in_chunk_samples = std::max<int64_t>(((m_chunk - 1) * D + T + 63) / 64 * 64, by_stream ? (n_samples + 63) / 64 * 64 : 0);
     const size_t in_elem_bytes_num = packed ? 5 : 16, in_elem_den = 4;  // bytes per 4 samples
     const size_t in_row_bytes = (size_t)in_chunk_samples / in_elem_den * in_elem_bytes_num;
-    int rc = ensure_chunks(h, in_row_bytes * (size_t)n_streams + 64, (size_t)m_chunk * (size_t)n_streams);
+    int rc = ensure_chunks(h, in_row_bytes * (size_t)spc + 64, (size_t)m_chunk * (size_t)spc);
     if (rc) return rc;
     DrainGuard drain(h);
     const bool pageable_in = h->copy_threads > 0 && is_pageable(h_in);
@@ -589,30 +596,38 @@ int run_host(ddcb200* h, const void* h_in, bool packed, int64_t n_samples, int64
 
     for (int64_t c = 0; c < n_chunks; ++c) {
         const int b = (int)(c % ddcb200::kBufs);
-        const int64_t m0 = c * m_chunk;
+        const int64_t s0 = (c / n_tchunks) * spc;                       // first stream of this chunk
+        const int64_t ns = std::min<int64_t>(spc, n_streams - s0);      // its streams
+        const int64_t m0 = (c % n_tchunks) * m_chunk;
         const int64_t mc = std::min<int64_t>(m_chunk, M - m0);
         const int64_t n0 = m0 * D;
         const int64_t nc = (mc - 1) * D + T;                  // samples this chunk needs
         const int64_t nc4 = std::min<int64_t>((nc + 3) / 4 * 4, n_samples - n0);  // copy whole groups when available
-        const size_t row_bytes = packed ? (size_t)(nc4 / 4 * 5) : (size_t)nc4 * 4;
-        const size_t src_off = packed ? (size_t)(n0 / 4 * 5) : (size_t)n0 * 4;
         const size_t src_pitch = packed ? (size_t)in_stride : (size_t)in_stride * 4;
+        const int64_t ncopy = by_stream ? n_samples : nc4;       // by-stream chunks copy whole rows (flat when rows are contiguous)
+        const size_t row_bytes = packed ? (size_t)(ncopy / 4 * 5) : (size_t)ncopy * 4;
+        const bool flat_in = by_stream && src_pitch == row_bytes && row_bytes % 16 == 0;
+        const size_t src_off = (packed ? (size_t)(n0 / 4 * 5) : (size_t)n0 * 4) + (size_t)s0 * src_pitch;
         // buffer b is free once the D2H of chunk c - kBufs finished (ev_out) -- wait on the copy-in stream
         if (c >= ddcb200::kBufs) CUDA_TRY(cudaStreamWaitEvent(h->copy_in, h->ev_k[b], 0));
         if (n_streams == 1 && pageable_in && row_bytes >= (16u << 20)) {   // below that the thread start-up costs more than it saves
             rc = staged_h2d(h, h->d_chunk_in[b], reinterpret_cast<const char*>(h_in) + src_off, row_bytes, h->copy_in);
             if (rc) return rc;
         } else {
-            CUDA_TRY(copy_rows_async(h->d_chunk_in[b], in_row_bytes, reinterpret_cast<const char*>(h_in) + src_off, src_pitch,
-                                     row_bytes, (size_t)n_streams, cudaMemcpyHostToDevice, h->copy_in));
+            // whole contiguous rows (by-stream chunks): the device rows take the host pitch, so the group is ONE flat copy
+            const size_t dpitch = flat_in ? row_bytes : in_row_bytes;
+            CUDA_TRY(copy_rows_async(h->d_chunk_in[b], dpitch, reinterpret_cast<const char*>(h_in) + src_off, src_pitch,
+                                     row_bytes, (size_t)ns, cudaMemcpyHostToDevice, h->copy_in));
         }
         CUDA_TRY(cudaEventRecord(h->ev_in[b], h->copy_in));
         CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
         if (c >= ddcb200::kBufs) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_out[b], 0));
         const int64_t n_dev = packed ? (nc4 / 4 * 4) : nc;
-        rc = run_device(h, h->d_chunk_in[b], packed, packed ? nc4 : n_dev, n_streams,
-                        packed ? (int64_t)in_row_bytes : (int64_t)(in_row_bytes / 4), step, sample_offset + n0,
-                        h->d_chunk_out[b], m_chunk, h->stream, mc);
+        const size_t d_in_pitch = flat_in ? row_bytes : in_row_bytes;
+        const int64_t d_out_pitch = (by_stream && out_stride == mc) ? mc : m_chunk;   // contiguous host rows: one flat D2H
+        rc = run_device(h, h->d_chunk_in[b], packed, packed ? nc4 : n_dev, ns,
+                        packed ? (int64_t)d_in_pitch : (int64_t)(d_in_pitch / 4), step, sample_offset + n0,
+                        h->d_chunk_out[b], d_out_pitch, h->stream, mc);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(h->ev_k[b], h->stream));
         CUDA_TRY(cudaStreamWaitEvent(h->copy_out, h->ev_k[b], 0));
@@ -628,8 +643,8 @@ int run_host(ddcb200* h, const void* h_in, bool packed, int64_t n_samples, int64
             pend_mc = mc;
             pend_b = b;
         } else {
-            CUDA_TRY(copy_rows_async(h_out + m0, (size_t)out_stride * sizeof(ddcb200_c64), h->d_chunk_out[b],
-                                     (size_t)m_chunk * sizeof(ddcb200_c64), (size_t)mc * sizeof(ddcb200_c64), (size_t)n_streams,
+            CUDA_TRY(copy_rows_async(h_out + s0 * out_stride + m0, (size_t)out_stride * sizeof(ddcb200_c64), h->d_chunk_out[b],
+                                     (size_t)d_out_pitch * sizeof(ddcb200_c64), (size_t)mc * sizeof(ddcb200_c64), (size_t)ns,
                                      cudaMemcpyDeviceToHost, h->copy_out));
             CUDA_TRY(cudaEventRecord(h->ev_out[b], h->copy_out));
         }
@@ -997,6 +1012,11 @@ int ddcb200_set_option(ddcb200_t* h, const char* key, int64_t value) {
     if (!strcmp(key, "tc_ns")) {   // tuning: sub-streams of the tensor engine (0 = automatic)
         if (value != 0 && value != 8 && value != 16 && value != 32) return fail(DDCB200_EINVAL, "tc_ns must be 0, 8, 16 or 32");
         h->tc_ns = (int)value;
+        return DDCB200_OK;
+    }
+    if (!strcmp(key, "host_chunk_mode")) {   // 0: by stream when whole streams fit a chunk (default); 1: always time chunks
+        if (value != 0 && value != 1) return fail(DDCB200_EINVAL, "host_chunk_mode must be 0 or 1");
+        h->host_chunk_mode = (int)value;
         return DDCB200_OK;
     }
     if (!strcmp(key, "tc_na") || !strcmp(key, "tc_nraw")) {   // tuning: pipeline depths of the tensor engine (0 = automatic)

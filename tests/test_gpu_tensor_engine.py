@@ -218,3 +218,26 @@ def test_tensor_engine_two_streams_of_work_share_a_handle(taps_dir):
         torch.cuda.synchronize()
         for i in range(len(fcs)):
             assert torch.equal(got[i], want[i]), (rep, i)
+
+
+@pytest.mark.parametrize("packed", [False, True])
+@pytest.mark.parametrize("n,s", [(65_536, 7), (50_003 * 4, 5), (1 << 20, 2)])
+def test_host_path_by_stream_chunks_equal_time_chunks(n, s, packed, taps_dir):
+    """The host entry points cut a batch of short streams BY STREAM (whole rows per chunk, flat copies) and long streams in
+    TIME; both chunkings, several chunk budgets, contiguous and odd row lengths must give the one-shot device result."""
+    ddc = DigitalDownConverter(16, FS, os.path.join(taps_dir, "ddc_coeff_107MHz.csv"))
+    xs = np.stack([synth.digitiser_stream_fast(n, 40 + k, block=min(n, 1 << 16)) for k in range(s)])
+    if packed:
+        host = np.stack([synth.pack10(r) for r in xs])
+        want = ddc.run_tensor(torch.from_numpy(host).cuda(), 100e6, packed=True).cpu().numpy()
+        run = lambda: ddc.run_batch_packed(host, 100e6)   # noqa: E731
+    else:
+        host = xs.astype(np.float32)
+        want = ddc.run_tensor(torch.from_numpy(host).cuda(), 100e6).cpu().numpy()
+        run = lambda: ddc.run_batch(host, 100e6)   # noqa: E731
+    scale = np.abs(want).max()
+    for mode, chunk in ((0, 1 << 24), (0, 3 * n + 5), (0, n), (1, 1 << 24), (1, n // 3), (0, n // 3)):
+        ddc.set_option("host_chunk_mode", mode)
+        ddc.set_option("chunk_samples", chunk)
+        got = run()
+        assert got.shape == want.shape and np.abs(got - want).max() <= TOL_MAX * scale, (mode, chunk, np.abs(got - want).max() / scale)
