@@ -324,6 +324,11 @@ def run_ours(args):
             raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    if world > 1:   # fewer ranks than GPUs: deal the ranks over both host-bridge groups of the box (scheduler.py)
+        from dc_sand_b200.scheduler import device_for_local_rank
+
+        local = device_for_local_rank(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)), torch.cuda.device_count(),
+                                      os.environ.get("DDCB200_DEVICE_ORDER"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     numa_node = bind_to_gpu_numa(local) if world > 1 else None
@@ -527,6 +532,9 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "final_gather_ms_untimed": gather_ms,
             "numa_node_rank0": numa_node,
+            "device_rank0": local,
+            "device_placement": "ranks dealt alternately to the two halves of the box's devices when fewer ranks than devices "
+                                "(dc_sand_b200.scheduler.device_for_local_rank; profiles/r2_n8_placement.txt)",
             "clocks": clk.summary(),
         }
         if extra:

@@ -30,6 +30,30 @@ def shard_range(n_streams: int, world_size: int, rank: int) -> tuple[int, int]:
     return start, start + base + (1 if rank < extra else 0)
 
 
+def device_for_local_rank(local_rank: int, local_world: int, n_devices: int, order: str | None = None) -> int:
+    """CUDA device of a rank when FEWER ranks than devices share a box.
+
+    The GPUs of an 8 x B200 box hang off two groups of host bridges (devices 0 .. 3 and 4 .. 7), and the host link is what
+    bounds the end-to-end path: four ranks on devices 0 .. 3 get 100 GB/s between them, on 0, 4, 1, 5 they get 164 GB/s
+    (profiles/r2_n8_placement.txt).  So ranks are dealt alternately to the two halves: 0, n/2, 1, n/2 + 1, ...  With as many
+    ranks as devices it is the identity.  `order` ("4,5,6,7,0,1,2,3", or the environment variable DDCB200_DEVICE_ORDER in
+    bench.py) overrides the rule."""
+    if not (0 <= local_rank < local_world):
+        raise ValueError(f"bad local rank {local_rank} of {local_world}")
+    if order:
+        devs = [int(v) for v in order.split(",")]
+        if len(set(devs)) != len(devs) or len(devs) < local_world or any(not (0 <= d < n_devices) for d in devs):
+            raise ValueError(f"device order {order!r} does not name {local_world} distinct devices below {n_devices}")
+        return devs[local_rank]
+    if local_world >= n_devices or n_devices < 2:
+        if local_rank >= max(n_devices, 1):
+            raise ValueError(f"local rank {local_rank} has no device ({n_devices} visible)")
+        return local_rank
+    half = (n_devices + 1) // 2
+    dealt = [d for pair in zip(range(half), range(half, 2 * half)) for d in pair if d < n_devices]
+    return dealt[local_rank]
+
+
 def shard_sizes(n_streams: int, world_size: int) -> list[int]:
     return [b - a for a, b in (shard_range(n_streams, world_size, r) for r in range(world_size))]
 

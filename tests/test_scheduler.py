@@ -79,3 +79,26 @@ def test_run_local_checks_shard_size():
     assert list(sh.local_streams) == [4, 5, 6, 7]
     with pytest.raises(ValueError):
         sh.run_local(torch.zeros(3, 16))
+
+
+def test_device_placement_deals_ranks_over_both_halves():
+    """Fewer ranks than devices: ranks alternate between the two host-bridge groups (0 .. n/2 - 1 and n/2 .. n - 1); as many
+    ranks as devices: identity; an explicit order overrides; every rank of a job gets a distinct device."""
+    from dc_sand_b200.scheduler import device_for_local_rank as dev
+
+    assert [dev(r, 2, 8) for r in range(2)] == [0, 4]
+    assert [dev(r, 4, 8) for r in range(4)] == [0, 4, 1, 5]
+    assert [dev(r, 8, 8) for r in range(8)] == list(range(8))
+    assert [dev(r, 3, 4) for r in range(3)] == [0, 2, 1]
+    assert [dev(r, 2, 3) for r in range(2)] == [0, 2]
+    assert dev(0, 1, 1) == 0 and dev(0, 1, 8) == 0
+    for n_dev in range(1, 9):
+        for world in range(1, n_dev + 1):
+            got = [dev(r, world, n_dev) for r in range(world)]
+            assert len(set(got)) == world and all(0 <= d < n_dev for d in got), (n_dev, world, got)
+    assert [dev(r, 4, 8, "4,5,6,7,0,1,2,3") for r in range(4)] == [4, 5, 6, 7]
+    for bad in ("0,0,1,2", "0,1", "0,1,2,9"):
+        with pytest.raises(ValueError):
+            dev(0, 4, 8, bad)
+    with pytest.raises(ValueError):
+        dev(4, 4, 8)

@@ -28,6 +28,8 @@ from dc_sand_b200 import DigitalDownConverter, _lib, taps  # noqa: E402
 def main():
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    if os.environ.get("E2E_DEVICES"):                       # placement experiment: local rank -> device index
+        local = int(os.environ["E2E_DEVICES"].split(",")[local])
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("gloo")
@@ -76,6 +78,8 @@ def main():
 
     cases = [("bare", bare), ("bare16", bare16), ("e2e_time", e2e_mode(1, 1 << 24)), ("e2e_stream", e2e_mode(0, 1 << 24)),
              ("e2e_big", e2e_mode(0, 1 << 26))]
+    if os.environ.get("E2E_CASES"):
+        cases = [c for c in cases if c[0] in os.environ["E2E_CASES"].split(",")]
     rows = []
     for name, fn in cases:
         if hasattr(fn, "setup"):
@@ -100,6 +104,7 @@ def main():
         allrows = [rows]
     if rank == 0:
         gib = s * n * 4 / 2**30
+        print(f"# devices {os.environ.get('E2E_DEVICES', 'identity')}")
         print(f"# {world} rank(s), each {gib:.0f} GiB H2D + {s * m * 8 / 2**20:.0f} MiB D2H per step; ms per step per rank (burst = median of 3 "
               "barrier-started single steps, sustained = 5 back-to-back steps after one barrier)")
         for i, (name, *_rest) in enumerate(rows):
