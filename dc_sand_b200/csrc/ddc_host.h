@@ -98,9 +98,7 @@ int make_slice_tmap(const float* d_in, int D, bool whole, int slot_rows, long lo
 // ---- kernel launchers, one translation unit per family (k_*.cu); D / jt are checked by the dispatcher -----------------
 int launch_tile(ddcb200* h, RunParams& p, const float2* ctaps, cudaStream_t st, int D, int ks);                       // k_tile.cu
 int launch_pd(ddcb200* h, RunParams& p, const float2* ctaps, cudaStream_t st, int D, int jt);                         // k_pd.cu
-int launch_p10(ddcb200* h, RunParams& p, const float2* ctaps, cudaStream_t st, int D, int jt);                        // k_pd.cu
 int launch_w(ddcb200* h, RunParams& p, cudaStream_t st, double step, int D, int jt);                                  // k_w.cu
-int launch_w10(ddcb200* h, RunParams& p, cudaStream_t st, double step, int D, int jt);                                // k_w10.cu
 int launch_w10s(ddcb200* h, RunParams& p, cudaStream_t st, double step);                                              // k_w10.cu
 bool tc10_supported(const ddcb200* h, int n_taps, int D);                                                                               // k_tc.cu
 int launch_tc10(ddcb200* h, RunParams& p, cudaStream_t st, double step, int D);                                       // k_tc.cu

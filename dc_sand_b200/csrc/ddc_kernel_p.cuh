@@ -323,203 +323,4 @@ ddc_fused_pd_kernel(const __grid_constant__ RunParams p, const __grid_constant__
     }
 }
 
-// =============================================================================================================
-// Packed 10-bit input (BASELINE configs[2]; reference stub ddc.py:68-83): the same phase-major FIR, but the ring holds
-// the RAW packed chunk (5 bytes per 4 samples: 5440 B instead of 17 KB, so 16 chunks fit and a chunk is ONE bulk copy)
-// and every warp group owns a private float staging buffer into which it unpacks its chunk before the FIR:
-//      TMA (raw bytes) -> raw ring -> [warp: PRMT/SHF/I2F unpack, bit-exact] -> private padded float rows -> FIR.
-// Format: big-endian bit stream, sample k at bits [10k, 10k+10), two's complement.
-// =============================================================================================================
-template <int D, int JT>
-struct P10Cfg : PCfg<D, JT, 1> {
-    using B = PCfg<D, JT, 1>;
-    static constexpr int RAW_BYTES = B::TOT_ROWS * B::ROW / 4 * 5;                 // 5440 for 34 rows
-    static constexpr int FLOAT_BYTES = B::NGROUPS * B::SLOT_FLOATS * 4;            // private buffers
-    static constexpr int NRAW_MAX = (227 * 1024 - 512 - FLOAT_BYTES) / RAW_BYTES;
-    static constexpr int NRAW = NRAW_MAX > 16 ? 16 : NRAW_MAX;
-    static_assert(RAW_BYTES % 16 == 0, "raw chunk must be a whole number of 16-byte groups");
-    static_assert(NRAW >= B::NGROUPS + 2, "raw ring too small");
-    __host__ __device__ static constexpr int sub_count(int pr) { return B::NPROD == 1 ? NRAW : (pr == 0 ? (NRAW + 1) / 2 : NRAW / 2); }
-    __host__ __device__ static constexpr int sub_base(int pr) { return (B::NPROD == 1 || pr == 0) ? 0 : (NRAW + 1) / 2; }
-};
-
-template <int D, int JT, int MAXT>
-__global__ void __launch_bounds__(P10Cfg<D, JT>::NWARPS * 32 + 32 * P10Cfg<D, JT>::NPROD, 1)
-ddc_fused_p10_kernel(const __grid_constant__ RunParams p, const __grid_constant__ TapsParam<MAXT> taps) {
-    using C = P10Cfg<D, JT>;
-    constexpr int ROW = C::ROW, R = C::R, NW = C::NW, NWARPS = C::NWARPS, NG = C::NGROUPS;
-    constexpr int NRAW = C::NRAW, RAWB = C::RAW_BYTES;
-    constexpr int WANT = C::TOT_ROWS * ROW;   // samples staged per chunk
-
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);          // [16]
-    uint64_t* empty_bar = full_bar + 16;                                 // [16]
-    volatile int* slot_seq = reinterpret_cast<volatile int*>(smem_raw + 384);
-    float* fbuf = reinterpret_cast<float*>(smem_raw + 512);              // NG private float buffers
-    unsigned char* rbuf = smem_raw + 512 + C::FLOAT_BYTES;               // NRAW raw slots
-
-    const int tid = threadIdx.x;
-    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const int lane = tid & 31;
-    if (tid == 0) {
-#pragma unroll 1
-        for (int s = 0; s < NRAW; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
-            slot_seq[s] = -1;
-        }
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    const int cps = (int)p.tiles_per_stream;
-    const int n_k = (int)((p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
-    const unsigned long long chunk_dph = (unsigned long long)((long long)C::CHUNK_OUT * D) * p.step_fx;
-
-    if (warp >= NWARPS) {
-        // ------------------------------------------------------------------ producer warps (one bulk copy per chunk)
-        constexpr int NP = C::NPROD;
-        const int pid = warp - NWARPS;
-        const long long pstride = (long long)NP * gridDim.x;
-        const int gs = (int)(pstride / cps), gc = (int)(pstride % cps);
-        const long long pfirst = blockIdx.x + (long long)pid * gridDim.x;
-        int cs = (int)(pfirst / cps), cc = (int)(pfirst % cps);
-        const int sbase = C::sub_base(pid), scnt = C::sub_count(pid);
-        int sidx = 0;
-        uint32_t par = 1;
-        for (int k = pid; k < n_k; k += NP) {
-            const int slot = sbase + sidx;
-            if (lane == 0) {
-                mbar_wait(&empty_bar[slot], par);
-                slot_seq[slot] = k;
-            }
-            __syncwarp();
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(p.in) + (long long)cs * p.in_stride +
-                                       (long long)cc * (C::CHUNK_S / 4 * 5);
-            unsigned char* dst = rbuf + (size_t)slot * RAWB;
-            const long long valid = p.n_samples - (long long)cc * C::CHUNK_S;   // samples (multiple of 4)
-            if (valid >= WANT) {
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)RAWB);
-                    bulk_g2s(dst, src, (uint32_t)RAWB, &full_bar[slot]);
-                }
-            } else {
-                const int vb = (int)(valid > 0 ? valid / 4 * 5 : 0);   // valid bytes
-                const int bulk = vb & ~15;
-                for (int e = bulk + lane; e < RAWB; e += 32) dst[e] = (e < vb) ? src[e] : (unsigned char)0;
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)bulk);
-                    if (bulk > 0) bulk_g2s(dst, src, (uint32_t)bulk, &full_bar[slot]);
-                }
-            }
-            __syncwarp();
-            if (++sidx == scnt) { sidx = 0; par ^= 1u; }
-            cs += gs;
-            cc += gc;
-            if (cc >= cps) { cc -= cps; ++cs; }
-        }
-    } else {
-        // ------------------------------------------------------------------ compute warps
-        const int grp = warp;
-        const int g = (lane & 7) * C::SROWS + (lane >> 3);
-        int rowoff[C::HALO_ROWS + 1];
-#pragma unroll
-        for (int h = 0; h <= C::HALO_ROWS; ++h) rowoff[h] = C::row_offset(g + h);
-        float2 rot_thr[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) rot_thr[r] = nco_rot((unsigned long long)((long long)(g * R + r) * D) * p.step_fx);
-        float* sbuf = fbuf + (size_t)grp * C::SLOT_FLOATS;
-
-        const long long kstride = (long long)NG * gridDim.x;
-        const int gs = (int)(kstride / cps), gc = (int)(kstride % cps);
-        const long long first = blockIdx.x + (long long)grp * gridDim.x;
-        int cs = (int)(first / cps), cc = (int)(first % cps);
-        const int sbase = C::sub_base(grp % C::NPROD), scnt = C::sub_count(grp % C::NPROD);
-        int sidx = (grp / C::NPROD) % scnt;
-        uint32_t par = (uint32_t)((grp / C::NPROD) / scnt) & 1u;
-        for (int k = grp; k < n_k; k += NG) {
-            const int slot = sbase + sidx;
-            while (slot_seq[slot] != k) {}
-            mbar_wait(&full_bar[slot], par);
-            // ---- unpack: 16 samples (20 bytes) per step and lane; integer work, bit-exact
-            const uint32_t* rw = reinterpret_cast<const uint32_t*>(rbuf + (size_t)slot * RAWB);
-            constexpr int NSG = WANT / 16;   // 16-sample groups per chunk (272)
-            for (int sg = lane; sg < NSG; sg += 32) {
-                uint32_t w[5];
-#pragma unroll
-                for (int i = 0; i < 5; ++i) w[i] = __byte_perm(rw[sg * 5 + i], 0, 0x0123);   // big-endian words
-                float v[16];
-#pragma unroll
-                for (int s16 = 0; s16 < 16; ++s16) {
-                    const int bit = 10 * s16, wi = bit >> 5, sh = bit & 31;
-                    // sample left-aligned in a 32-bit word, then arithmetic shift sign-extends the 10 bits
-                    const uint32_t top = (sh <= 22) ? (w[wi] << sh) : __funnelshift_l(w[wi + 1 > 4 ? 4 : wi + 1], w[wi], sh);
-                    v[s16] = (float)((int)top >> 22);
-                }
-                const int n = sg * 16, row = n / ROW, col = n % ROW;
-                float4* d4 = reinterpret_cast<float4*>(sbuf + C::row_offset(row) + col);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) d4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[slot]);   // raw slot back to the producer
-
-            float2 acc[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] = make_float2(0.f, 0.f);
-            int xoff = 0;
-            const float4* tp = &taps.c2[0];
-#pragma unroll 1
-            for (int pg = 0; pg < C::V; ++pg, tp += 2) {
-                asm volatile("" : "+r"(xoff));
-                float4 w[NW];
-#pragma unroll
-                for (int b = 0; b < NW; ++b)
-                    w[b] = *reinterpret_cast<const float4*>(sbuf + xoff + rowoff[b / R] + (b % R) * D);
-                xoff += 4;
-#pragma unroll
-                for (int j = 0; j < JT; ++j) {
-                    const float4 ta = tp[j * (D / 2)], tb = tp[j * (D / 2) + 1];
-#pragma unroll
-                    for (int r = 0; r < R; ++r) acc[r] = ffma2(w[r + j].x, make_float2(ta.x, ta.y), acc[r]);
-#pragma unroll
-                    for (int r = 0; r < R; ++r) acc[r] = ffma2(w[r + j].y, make_float2(ta.z, ta.w), acc[r]);
-#pragma unroll
-                    for (int r = 0; r < R; ++r) acc[r] = ffma2(w[r + j].z, make_float2(tb.x, tb.y), acc[r]);
-#pragma unroll
-                    for (int r = 0; r < R; ++r) acc[r] = ffma2(w[r + j].w, make_float2(tb.z, tb.w), acc[r]);
-                }
-            }
-            __syncwarp();   // every lane is done with the private buffer before the next unpack overwrites it
-
-            const float2 rot_chunk = nco_rot(p.phase0_fx + (unsigned long long)cc * chunk_dph);
-            const long long m0 = (long long)cc * C::CHUNK_OUT + g * R;
-            float2* o = p.out + (long long)cs * p.out_stride + m0;
-            float2 y[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) y[r] = cmul(cmul(acc[r], rot_thr[r]), rot_chunk);
-            if (m0 + R <= p.n_out) {
-                if (p.vec_store && (R % 2 == 0)) {
-#pragma unroll
-                    for (int r = 0; r < R; r += 2)
-                        __stcs(reinterpret_cast<float4*>(o + r), make_float4(y[r].x, y[r].y, y[r + 1].x, y[r + 1].y));
-                } else {
-#pragma unroll
-                    for (int r = 0; r < R; ++r) __stcs(o + r, y[r]);
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < R; ++r)
-                    if (m0 + r < p.n_out) __stcs(o + r, y[r]);
-            }
-            sidx += NG / C::NPROD;
-            if (sidx >= scnt) { sidx -= scnt; par ^= 1u; }
-            cs += gs;
-            cc += gc;
-            if (cc >= cps) { cc -= cps; ++cs; }
-        }
-    }
-}
-
 }  // namespace ddck

@@ -1,5 +1,7 @@
-// Packed 10-bit input on the fast-FIR machinery of ddc_kernel_w.cuh: the fused-unpack kernel (every compute warp unpacks its
-// own chunk) and the warp-specialised kernel (unpack warps -> float ring -> FIR warps).
+// Packed 10-bit input on the fast-FIR machinery of ddc_kernel_w.cuh, CUDA cores: the warp-specialised kernel (unpack warps ->
+// float ring -> FIR warps).  Since round 2 the default engine for packed input is the tensor-core one (ddc_kernel_tc.cuh); this
+// kernel is what option packed_engine = 0 selects at D = 16, 129 .. 256 taps (other cells: unpack stage + float32 kernel).  The
+// in-warp-unpack variants of round 1 (fast FIR and direct form, D = 16 / 32 / 64) were measured slower than both and are gone.
 #pragma once
 #include "ddc_kernel_w.cuh"
 
@@ -18,242 +20,15 @@ namespace ddck {
 // stored ROTATED by (c >> 1): logical unit u lives at physical unit (u + (c >> 1)) & 3.  Writers become conflict-free;
 // FIR readers (all lanes read the same block and unit of different rows) only see a different constant offset.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int D, int JT>
-struct W10Cfg : P10Cfg<D, JT> {
-    using B = PCfg<D, JT, 1>;
-    static_assert(JT % 2 == 0 && B::R % 2 == 0, "fast FIR needs an even number of tap blocks and outputs per thread");
-    static constexpr int JH = JT / 2, RH = B::R / 2;
-    static constexpr int NTW = 3 * JH * D;
-    // physical float offset inside a row of the 16-byte unit that logically starts at float offset fo (multiple of 4)
-    __host__ __device__ static constexpr int rot_off(int fo) { return (fo & ~15) + 4 * ((((fo >> 2) & 3) + ((fo >> 5) & 3)) & 3); }
-};
-
 __device__ __forceinline__ float unpack10_bits(uint32_t field, uint32_t k4b000200) {   // field: the 10 bits in [9:0], anything above
     uint32_t bits;   // (field & 0x3FF) ^ 0x4B000200 as ONE LOP3 (the constant must sit in a register for that)
     asm("lop3.b32 %0, %1, 0x3FF, %2, 0x6A;" : "=r"(bits) : "r"(field), "r"(k4b000200));
     return __uint_as_float(bits);   // = 2^23 + 512 + v; the caller subtracts 8389120 (two samples per FADD2)
 }
 
-template <int D, int JT>
-__global__ void __launch_bounds__(W10Cfg<D, JT>::NWARPS * 32 + 32 * W10Cfg<D, JT>::NPROD, 1)
-ddc_fused_w10_kernel(const __grid_constant__ RunParams p, const __grid_constant__ TapsParam<W10Cfg<D, JT>::NTW> taps) {
-    using C = W10Cfg<D, JT>;
-    constexpr int ROW = C::ROW, R = C::R, NW = C::NW, NWARPS = C::NWARPS, NG = C::NGROUPS;
-    constexpr int NRAW = C::NRAW, RAWB = C::RAW_BYTES, RH = C::RH;
-    constexpr int WANT = C::TOT_ROWS * ROW;   // samples staged per chunk
-
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);          // [16]
-    uint64_t* empty_bar = full_bar + 16;                                 // [16]
-    volatile int* slot_seq = reinterpret_cast<volatile int*>(smem_raw + 384);
-    float* fbuf = reinterpret_cast<float*>(smem_raw + 512);              // NG private float buffers
-    unsigned char* rbuf = smem_raw + 512 + C::FLOAT_BYTES;               // NRAW raw slots
-
-    const int tid = threadIdx.x;
-    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const int lane = tid & 31;
-    if (tid == 0) {
-#pragma unroll 1
-        for (int s = 0; s < NRAW; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
-            slot_seq[s] = -1;
-        }
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    const int cps = (int)p.tiles_per_stream;
-    const int n_k = (int)((p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
-    const unsigned long long chunk_dph = (unsigned long long)((long long)C::CHUNK_OUT * D) * p.step_fx;
-
-    if (warp >= NWARPS) {
-        // ------------------------------------------------------------------ producer warps (one bulk copy per chunk)
-        constexpr int NP = C::NPROD;
-        const int pid = warp - NWARPS;
-        const long long pstride = (long long)NP * gridDim.x;
-        const int gs = (int)(pstride / cps), gc = (int)(pstride % cps);
-        const long long pfirst = blockIdx.x + (long long)pid * gridDim.x;
-        int cs = (int)(pfirst / cps), cc = (int)(pfirst % cps);
-        const int sbase = C::sub_base(pid), scnt = C::sub_count(pid);
-        int sidx = 0;
-        uint32_t par = 1;
-        for (int k = pid; k < n_k; k += NP) {
-            const int slot = sbase + sidx;
-            if (lane == 0) {
-                mbar_wait(&empty_bar[slot], par);
-                slot_seq[slot] = k;
-            }
-            __syncwarp();
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(p.in) + (long long)cs * p.in_stride +
-                                       (long long)cc * (C::CHUNK_S / 4 * 5);
-            unsigned char* dst = rbuf + (size_t)slot * RAWB;
-            const long long valid = p.n_samples - (long long)cc * C::CHUNK_S;   // samples (multiple of 4)
-            if (valid >= WANT) {
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)RAWB);
-                    bulk_g2s(dst, src, (uint32_t)RAWB, &full_bar[slot]);
-                }
-            } else {
-                const int vb = (int)(valid > 0 ? valid / 4 * 5 : 0);   // valid bytes
-                const int bulk = vb & ~15;
-                for (int e = bulk + lane; e < RAWB; e += 32) dst[e] = (e < vb) ? src[e] : (unsigned char)0;
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)bulk);
-                    if (bulk > 0) bulk_g2s(dst, src, (uint32_t)bulk, &full_bar[slot]);
-                }
-            }
-            __syncwarp();
-            if (++sidx == scnt) { sidx = 0; par ^= 1u; }
-            cs += gs;
-            cc += gc;
-            if (cc >= cps) { cc -= cps; ++cs; }
-        }
-    } else {
-        // ------------------------------------------------------------------ compute warps
-        const int grp = warp;
-        const int g = (lane & 7) * C::SROWS + (lane >> 3);
-        int rowoff[C::HALO_ROWS + 1];
-#pragma unroll
-        for (int h = 0; h <= C::HALO_ROWS; ++h) rowoff[h] = C::row_offset(g + h);
-        float2 rot_thr[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) rot_thr[r] = nco_rot((unsigned long long)((long long)(g * R + r) * D) * p.step_fx);
-        float* sbuf = fbuf + (size_t)grp * C::SLOT_FLOATS;
-
-        const long long kstride = (long long)NG * gridDim.x;
-        const int gs = (int)(kstride / cps), gc = (int)(kstride % cps);
-        const long long first = blockIdx.x + (long long)grp * gridDim.x;
-        int cs = (int)(first / cps), cc = (int)(first % cps);
-        const int sbase = C::sub_base(grp % C::NPROD), scnt = C::sub_count(grp % C::NPROD);
-        int sidx = (grp / C::NPROD) % scnt;
-        uint32_t par = (uint32_t)((grp / C::NPROD) / scnt) & 1u;
-
-        float2 yprev[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) yprev[r] = make_float2(0.f, 0.f);
-        long long prev_m0 = 0;
-        float2* prev_o = p.out;
-        int prev_cc = 0;
-        long long prev_nout = 0;
-        float2 m0a[RH], m1a[RH], m2a[RH];
-        static_assert(D == 16 || D == 32 || D == 64, "unit rotation assumes whole 16-sample groups per block");
-        // where this lane's four 16-byte units of a 16-sample group go (floats, relative to the group): rotation by the
-        // index of the group within its 128-sample row, halved
-        int wr_unit[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) wr_unit[q] = 4 * ((q + ((lane & 7) >> 1)) & 3);
-        uint32_t kmagic = 0x4B000200u;
-        asm volatile("" : "+r"(kmagic));   // keep it in a register (see unpack10_f)
-
-        long long t_wait = 0;
-        const long long t_begin = clock64();
-        const int dm = p.debug_mode & 255;   // tuning aids: 3 = unpack only (no FIR), 4 = FIR only (no unpack)
-        for (int k = grp; k < n_k; k += NG) {
-            const int slot = sbase + sidx;
-            {
-                const long long tw0 = p.dbg ? clock64() : 0;
-                while (slot_seq[slot] != k) {}
-                mbar_wait(&full_bar[slot], par);
-                if (p.dbg) t_wait += clock64() - tw0;
-            }
-            // ---- unpack: 16 samples (20 bytes = 5 words) per step and lane; integer work, bit-exact
-            const uint32_t* rw = reinterpret_cast<const uint32_t*>(rbuf + (size_t)slot * RAWB);
-            constexpr int NSG = WANT / 16;   // 16-sample groups per chunk (272)
-            constexpr int UNPACK_UNROLL = DDCB200_W10_UNPACK_UNROLL;
-#pragma unroll UNPACK_UNROLL
-            for (int sg = lane; sg < (dm == 4 ? 0 : NSG); sg += 32) {
-                uint32_t w[5];
-#pragma unroll
-                for (int i = 0; i < 5; ++i) w[i] = __byte_perm(rw[sg * 5 + i], 0, 0x0123);   // big-endian words
-                float v[16];
-#pragma unroll
-                for (int s16 = 0; s16 < 16; ++s16) {
-                    // sample s16 occupies bits [10 s16, 10 s16 + 10) of the 160-bit big-endian group: right-align it
-                    const int bit = 10 * s16, wi = bit >> 5, sh = bit & 31;
-                    const uint32_t fld = (sh <= 22) ? (w[wi] >> (22 - sh)) : __funnelshift_r(w[wi + 1 > 4 ? 4 : wi + 1], w[wi], 54 - sh);
-                    v[s16] = unpack10_bits(fld, kmagic);
-                }
-#pragma unroll
-                for (int s16 = 0; s16 < 16; s16 += 2) {
-                    const float2 d = __fadd2_rn(make_float2(v[s16], v[s16 + 1]), make_float2(-8389120.0f, -8389120.0f));
-                    v[s16] = d.x;
-                    v[s16 + 1] = d.y;
-                }
-                // group sg = block (sg & 7) of row (sg >> 3); sg & 7 == lane & 7 in every step
-                float* blk = sbuf + C::row_offset(sg >> 3) + (lane & 7) * 16;
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    *reinterpret_cast<float4*>(blk + wr_unit[q]) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[slot]);   // raw slot back to the producer
-
-#pragma unroll
-            for (int r = 0; r < RH; ++r) m0a[r] = m1a[r] = m2a[r] = make_float2(0.f, 0.f);
-            int xoff = 0;
-            const float4* tp = &taps.c2[0];
-            if (dm != 3) {
-                float4 w[NW];
-#pragma unroll
-                for (int b = 0; b < NW; ++b)
-                    w[b] = *reinterpret_cast<const float4*>(sbuf + rowoff[b / R] + C::rot_off((b % R) * D));
-                w_epilogue<R>(yprev, rot_thr, p.phase0_fx + (unsigned long long)prev_cc * chunk_dph, prev_m0, prev_o, prev_nout);
-                w_fir_pg<D, JT, R>(w, tp, m0a, m1a, m2a);
-                xoff = 4;
-                tp += 2;
-            }
-#pragma unroll 1
-            for (int pg = 1; pg < (dm == 3 ? 0 : C::V); ++pg, tp += 2) {
-                asm volatile("" : "+r"(xoff));
-                int xrot[4];   // D = 16: physical float offset of logical unit xoff / 4 under rotation 0 .. 3
-#pragma unroll
-                for (int rt = 0; rt < 4; ++rt) xrot[rt] = (xoff + 4 * rt) & 12;
-                float4 w[NW];
-#pragma unroll
-                for (int b = 0; b < NW; ++b) {
-                    // float offset (b % R) D + xoff inside the row: 16-sample group ((b % R) D + xoff) / 16, unit (xoff / 4) & 3
-                    const int grp16 = ((b % R) * D) / 16;          // + xoff / 16, which is 0 for D = 16 (xoff < 16)
-                    if (D == 16) {
-                        w[b] = *reinterpret_cast<const float4*>(sbuf + rowoff[b / R] + grp16 * 16 + xrot[(grp16 >> 1) & 3]);
-                    } else {
-                        const int fo = (b % R) * D + xoff;
-                        w[b] = *reinterpret_cast<const float4*>(sbuf + rowoff[b / R] + (fo & ~15) + 4 * ((((fo >> 2) & 3) + ((fo >> 5) & 3)) & 3));
-                    }
-                }
-                xoff += 4;
-                w_fir_pg<D, JT, R>(w, tp, m0a, m1a, m2a);
-            }
-            __syncwarp();   // every lane is done with the private buffer before the next unpack overwrites it
-
-#pragma unroll
-            for (int r = 0; r < RH; ++r) {
-                yprev[2 * r] = make_float2(m0a[r].x + m1a[r].x, m0a[r].y + m1a[r].y);
-                yprev[2 * r + 1] = make_float2(m1a[r].x - m2a[r].x, m1a[r].y - m2a[r].y);
-            }
-            prev_cc = cc;
-            prev_m0 = (long long)cc * C::CHUNK_OUT + g * R;
-            prev_o = p.out + (long long)cs * p.out_stride + prev_m0;
-            prev_nout = p.n_out;
-
-            sidx += NG / C::NPROD;
-            if (sidx >= scnt) { sidx -= scnt; par ^= 1u; }
-            cs += gs;
-            cc += gc;
-            if (cc >= cps) { cc -= cps; ++cs; }
-        }
-        w_epilogue<R>(yprev, rot_thr, p.phase0_fx + (unsigned long long)prev_cc * chunk_dph, prev_m0, prev_o, prev_nout);
-        if (p.dbg && lane == 0) {
-            atomicAdd(p.dbg, (unsigned long long)t_wait);
-            atomicAdd(p.dbg + 1, (unsigned long long)(clock64() - t_begin));
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
-// Packed input, warp-specialised: in ddc_fused_w10_kernel every compute warp unpacks its own chunk and then filters it, so
-// the FMA pipe idles during the latency-bound unpack (0.19 of 1.13 ms).  Here FOUR UNPACK WARPS turn raw chunks into a
+// Packed input, warp-specialised: if every compute warp unpacks its own chunk and then filters it, the FMA pipe idles during
+// the latency-bound unpack (round 1: 0.19 of 1.13 ms).  Here FOUR UNPACK WARPS turn raw chunks into a
 // ring of float chunks (same rotated-unit layout) and EIGHT FIR WARPS consume them exactly like the float32 kernel; the
 // integer / LSU work of the unpackers runs under the FIR warps' FFMA2 stream.
 //      TMA producer warp -> raw ring (NR x 5440 B) -> unpack warps -> float ring (NF x 17.1 KB) -> FIR warps -> HBM

@@ -142,7 +142,6 @@ ddc_fused_ws_kernel(const __grid_constant__ RunParams p, const __grid_constant__
     }
     __syncthreads();
 
-    const int cps = (int)p.tiles_per_stream;   // chunks per stream
     const int n_k = (int)((p.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // chunks of this CTA
     // positions of this CTA: full rounds of 8 chunks, the last round may be partial (position exists iff its chunk does)
     const int n_rounds = (n_k + NG - 1) / NG;

@@ -237,8 +237,8 @@ static inline bool aligned_f32(const void* d_in, int64_t in_stride, bool packed)
 }
 
 // Core dispatcher for device-resident data.  Option "variant" (ddcb200_set_option): 0 auto; 1 generic kernel; 2 / 3 tile kernel
-// without / with the tap split; 5 direct-form packed kernel; 7 fast FIR (ddc_kernel_w.cuh, also for D = 32 / 64 and the
-// fused-unpack packed kernel); 8 phase-major direct form; 10 warp-specialised packed kernel; 11 tensor-staged / sliced fast FIR.
+// without / with the tap split; 7 fast FIR (ddc_kernel_w.cuh, also for D = 32 / 64); 8 phase-major direct form; 10 warp-
+// specialised CUDA-core packed kernel; 11 tensor-staged / sliced fast FIR; 13 tensor-core engine for packed input.
 int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int64_t n_streams, int64_t in_stride,
                double step, int64_t sample_offset, ddcb200_c64* d_out, int64_t out_stride, cudaStream_t st,
                int64_t m_limit = -1) {
@@ -289,19 +289,12 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         (double)((M + 127) / 128) * (double)n_streams < 2.0e9)
         return ddch::launch_tc10(h, p, st, step, D);
 
-    // ---- packed 10-bit input with the unpack fused behind the TMA ring (D = 16 / 32 / 64, up to 16 tap blocks) --------
-    if (packed && (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (in_stride % 16 == 0) && (D == 16 || D == 32 || D == 64) &&
-        Jp <= 16 && fv != 1) {
-        const int jt = Jp <= 4 ? 4 : (Jp <= 8 ? 8 : 16);
-        ring_geometry(jt);
-        // warp-specialised kernel (unpack warps + FIR warps): 1.10 against 1.13 ms on 64 x 2^24 samples; default where it is
-        // instantiated (D = 16, 129 .. 256 taps).  Fast FIR with in-warp unpack where a thread has R = 8 outputs (D = 16), direct
-        // form at D = 32 / 64.
-        if (D == 16 && jt == 16 && (fv == 10 || fv == 0)) return ddch::launch_w10s(h, p, st, step);
-        if ((D == 16 && fv != 5) || fv == 7) return ddch::launch_w10(h, p, st, step, D, jt);
-        std::vector<float2> ctp((size_t)jt * D);
-        make_ctaps(h, step, jt * D, ctp.data());
-        return ddch::launch_p10(h, p, ctp.data(), st, D, jt);
+    // ---- packed 10-bit input on the CUDA cores (option packed_engine = 0): warp-specialised fast-FIR kernel with the unpack fused
+    // behind the TMA ring where it is instantiated (D = 16, 129 .. 256 taps: 1.10 ms on 64 x 2^24 samples) -------------------------
+    if (packed && (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (in_stride % 16 == 0) && D == 16 && Jp > 8 && Jp <= 16 &&
+        (fv == 0 || fv == 10)) {
+        ring_geometry(16);
+        return ddch::launch_w10s(h, p, st, step);
     }
 
     // ---- packed input without a fused-unpack kernel for this (T, D): unpack into a float32 workspace, then the float32 path --

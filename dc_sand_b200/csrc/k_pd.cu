@@ -1,4 +1,4 @@
-// Launchers of the phase-major direct-form kernels (ddc_kernel_p.cuh): deferred-epilogue float32 kernel and packed-10-bit kernel.
+// Launchers of the phase-major direct-form kernels (ddc_kernel_p.cuh): the deferred-epilogue float32 kernel.
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -10,39 +10,6 @@ using namespace ddck;
 
 namespace ddch {
 namespace {
-template <int D, int JT>
-int launch_p10(ddcb200* h, RunParams& p, const float2* ctaps_host, cudaStream_t st) {
-    using C = P10Cfg<D, JT>;
-    constexpr int MAXT = JT * D;
-    auto kern = ddc_fused_p10_kernel<D, JT, MAXT>;
-    const size_t smem = 512 + (size_t)C::FLOAT_BYTES + (size_t)C::NRAW * C::RAW_BYTES;
-    static bool attr_set[64] = {};
-    if (h->device < 64 && !attr_set[h->device]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[h->device] = true;
-    }
-    TapsParam<MAXT> tp;
-    std::memset(&tp, 0, sizeof(tp));
-    std::memcpy(tp.c2, ctaps_host, sizeof(float2) * (size_t)std::min(p.n_taps, MAXT));
-    const long long grid = std::min<long long>(p.total_tiles, h->sm_count);
-    kern<<<(unsigned)grid, C::NWARPS * 32 + 32 * C::NPROD, smem, st>>>(p, tp);
-    CUDA_TRY(cudaGetLastError());
-    h->launches++;
-    char name[96];
-    snprintf(name, sizeof(name), "fused_phase_major_packed10<D%d,R%d,J%d,RAWSLOTS%d>", D, C::R, JT, C::NRAW);
-    h->last_variant = name;
-    return DDCB200_OK;
-}
-
-template <int D>
-int launch_p10_j(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, int jt) {
-    switch (jt) {
-        case 4: return launch_p10<D, 4>(h, p, ct, st);
-        case 8: return launch_p10<D, 8>(h, p, ct, st);
-        default: return launch_p10<D, 16>(h, p, ct, st);
-    }
-}
-
 template <int D, int JT>
 int launch_pd(ddcb200* h, RunParams& p, const float2* ctaps_host, cudaStream_t st) {
     using C = PCfg<D, JT, 1>;
@@ -84,15 +51,6 @@ int launch_pd(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, int D
         case 64: return launch_pd_j<64>(h, p, ct, st, jt);
     }
     return fail(DDCB200_EINVAL, "phase-major kernel: unsupported decimation %d", D);
-}
-
-int launch_p10(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, int D, int jt) {
-    switch (D) {
-        case 16: return launch_p10_j<16>(h, p, ct, st, jt);
-        case 32: return launch_p10_j<32>(h, p, ct, st, jt);
-        case 64: return launch_p10_j<64>(h, p, ct, st, jt);
-    }
-    return fail(DDCB200_EINVAL, "packed phase-major kernel: unsupported decimation %d", D);
 }
 
 }  // namespace ddch

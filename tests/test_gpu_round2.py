@@ -52,26 +52,27 @@ def _full_range_streams(n):
     return np.stack([a, b])
 
 
-# (D, T, variant option, expected kernel name fragment, bit-equal to the float32 kernel of the same loop?)
+# CUDA-core engine for packed input (option packed_engine = 0): (D, T, variant option, expected kernel name fragment,
+# bit-equal to the float32 kernel of the same loop?).  The in-warp-unpack kernels of round 1 (variants 5 and 7 on packed input)
+# were superseded by the tensor engine and removed; what is left is the warp-specialised kernel at D = 16, 129 .. 256 taps and
+# the bit-exact unpack stage in front of the float32 kernel of the cell everywhere else.
 FUSED_PACKED = [
     (16, 256, 0, "packed10_split", True),      # warp-specialised: unpack warps -> float ring -> the float32 kernel's FIR loop
-    (16, 256, 7, "fast_fir_packed10<", False),  # every compute warp unpacks its own chunk
-    (16, 256, 5, "phase_major_packed10", False),
-    (16, 100, 0, "fast_fir_packed10<", False),  # 8 tap blocks
-    (16, 40, 0, "fast_fir_packed10<", False),   # 4 tap blocks
-    (32, 256, 0, "packed10", False),
-    (32, 256, 7, "fast_fir_packed10<", False),
-    (32, 500, 5, "phase_major_packed10", False),
-    (64, 512, 0, "packed10", False),
-    (64, 1000, 7, "fast_fir_packed10<", False),
+    (16, 256, 10, "packed10_split", True),
+    (16, 200, 0, "packed10_split", False),     # 13 tap blocks padded to 16
+    (16, 100, 0, "unpack10+", False),          # 7 tap blocks: unpack stage + row-staged float32 kernel
+    (16, 1024, 0, "unpack10+", False),
+    (8, 256, 0, "unpack10+", False),
+    (32, 256, 0, "unpack10+", False),
+    (64, 1000, 0, "unpack10+", False),
 ]
 
 
 @pytest.mark.parametrize("d,t,variant,name,bit_equal", FUSED_PACKED)
 def test_fused_unpack_kernels_full_code_range(d, t, variant, name, bit_equal, tmp_path):
-    """north_star: bit-exact unpack.  The fused kernels never materialise the unpacked samples, so exactness is shown through
-    the outputs: with the FIR loop shared (warp-specialised kernel vs the float32 fast-FIR kernel) the packed and the float32
-    runs must be bit-identical; everywhere they must agree with the reference arithmetic on the unpacked samples."""
+    """north_star: bit-exact unpack, CUDA-core engine.  The fused kernel never materialises the unpacked samples, so exactness
+    is shown through the outputs: with the FIR loop shared (warp-specialised kernel vs the float32 fast-FIR kernel) the packed
+    and the float32 runs must be bit-identical; everywhere they must agree with the reference arithmetic on the unpacked samples."""
     from scipy import signal
 
     n = 64 * 4096 + 4096 + 320        # several chunks per CTA row, ragged last chunk, rows stay 16-byte aligned (n % 64 == 0)
@@ -83,7 +84,7 @@ def test_fused_unpack_kernels_full_code_range(d, t, variant, name, bit_equal, tm
     ddc.set_option("variant", variant)
     ddc.set_option("packed_engine", 0)   # the CUDA-core kernels (the tensor engine, default since round 2: test_gpu_tensor_engine.py)
     yp = ddc.run_tensor(torch.from_numpy(packed).cuda(), 100e6, packed=True)
-    assert name in ddc.last_variant and "unpack10+" not in ddc.last_variant, ddc.last_variant
+    assert name in ddc.last_variant and "tensor_fir" not in ddc.last_variant, ddc.last_variant
     ddc.set_option("variant", 0)
     yf = ddc.run_tensor(torch.from_numpy(xs.astype(np.float32)).cuda(), 100e6)
     if bit_equal:
