@@ -241,3 +241,35 @@ def test_host_path_by_stream_chunks_equal_time_chunks(n, s, packed, taps_dir):
         ddc.set_option("chunk_samples", chunk)
         got = run()
         assert got.shape == want.shape and np.abs(got - want).max() <= TOL_MAX * scale, (mode, chunk, np.abs(got - want).max() / scale)
+
+
+def test_tensor_engine_fuzz(tmp_path):
+    """Seeded random (T, D, N, streams, fc) on packed input: filters shorter than the decimation, two taps, tap counts that are
+    no multiple of anything, lengths from a single output to several tiles.  Guards the geometry seams of the engine (row
+    width 64 / 128, K padding, ragged last tile, halo shorter than a row when T < D)."""
+    from scipy import signal
+
+    rng = np.random.default_rng(20261019)
+    seen = set()
+    for case in range(40):
+        d = int(rng.choice([4, 8, 16, 32, 64]))
+        t = int(rng.choice([2, 3, rng.integers(3, 40), rng.integers(40, 300), rng.integers(300, 1400), 64, 256, 1024]))   # a one-line CSV loads as a 0-d array, in the reference too
+        streams = int(rng.integers(1, 5))
+        n = max(t, int(rng.integers(1, 3000)) * 64)         # rows stay 16-byte aligned
+        n = (n + 63) // 64 * 64
+        fc = float(rng.choice([100e6, 53.5e6, 428e6, 1.0e6, 855e6]))
+        tp = signal.firwin(t, min(0.8 / d, 0.99)) if t > 3 else np.ones(t)
+        ddc = DigitalDownConverter(d, FS, _custom_taps(tmp_path, tp))
+        xs = np.stack([synth.digitiser_stream(n, 2000 + case * 7 + s) for s in range(streams)])
+        if case % 3 == 0:
+            xs = _full_range_streams(n)[:1]
+        y = _run_packed(ddc, xs, fc=fc).cpu().numpy()
+        seen.add(ddc.last_variant.split(",K")[0])
+        ref = np.stack([orc.ddc_reference(r.astype(np.float32), fc, tp, d, FS) for r in xs])
+        assert y.shape == ref.shape, (case, d, t, n, y.shape, ref.shape)
+        emax, el2 = rel_err(y, ref)
+        k = 4 if t > 256 else 1
+        assert emax <= k * TOL_MAX and el2 <= k * TOL_L2, (case, d, t, n, streams, fc, ddc.last_variant, emax, el2)
+        ddc.close()
+    print("engine geometries exercised:", sorted(seen))
+    assert sum("tensor_fir" in v for v in seen) >= 6, seen
