@@ -341,12 +341,12 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
     //   D = 8: T = 64 0.054 vs 0.062, 128 0.070 vs 0.083, 256 0.122 vs 0.141, 512 0.229 vs 0.265, 1024 0.449 vs 0.545.
     //   D = 16: whole-row tiles for the HBM-bound filters only (T <= 128: 0.0517 against 0.0524 / 0.0537 ms of the 1-D bulk-copy
     //   kernel); longer filters are much slower here than in ddc_kernel_w.cuh (T = 256: 0.312 vs 0.244 ms at 2^28).
-    // The kernel pads the filter to 8, 16 or a multiple of 16 tap blocks, the tile kernel to a multiple of its R (16 / 8 at
+    // The kernel pads the filter to 8, 16, 32, 48, 64 or a multiple of 32 tap blocks, the tile kernel to a multiple of its R (16 / 8 at
     // D = 4 / 8): auto only where the padded work is within 12 % of the tile kernel's (its deficit there: 84-94 % against 99 %).
     if (aligned && pow2_d && fv != 1) {
         const int r_tile = 64 / D;   // outputs per thread of the tile kernel
         const bool fp32_bound = 4.0 * T / D > 11.4 * (4.0 + 8.0 / D);
-        const int jt_ws = Jp <= 8 ? 8 : (Jp + 15) / 16 * 16;
+        const int jt_ws = Jp <= 8 ? 8 : (Jp <= 64 ? (Jp + 15) / 16 * 16 : (Jp + 31) / 32 * 32);   // the instantiations of k_ws.inc
         const int j_tile = (Jp + r_tile - 1) / r_tile * r_tile;
         const bool pad_ok = jt_ws * 100 <= j_tile * 112;
         const bool auto_ws = (D == 4 && T <= 1024 && pad_ok) || (D == 8 && T <= 1024 && pad_ok) || (D == 16 && T <= 128) ||
@@ -373,14 +373,12 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         }
     }
 
-    // ---- ring kernels on 1-D bulk copies: fast FIR (D = 16, up to 64 tap blocks) / phase-major direct form (D = 32, 64) -----
-    if (!fused_done && aligned && (D == 16 || D == 32 || D == 64) && (Jp <= 16 || (D == 16 && Jp <= 64)) &&
-        (fv == 0 || fv == 7 || fv == 8)) {
+    // ---- ring kernels on 1-D bulk copies: fast FIR (D = 16, up to 64 tap blocks) / phase-major direct form (D = 32, 64, up to
+    // 16 tap blocks: the HBM-bound cells there; the FP32-bound ones went to the sliced kernel above) -----------------------------
+    if (!fused_done && aligned && ((D == 16 && Jp <= 64) || ((D == 32 || D == 64) && Jp <= 16)) && (fv == 0 || fv == 7 || fv == 8)) {
         const int jt = Jp <= 4 ? 4 : (Jp <= 8 ? 8 : (Jp <= 16 ? 16 : (Jp <= 32 ? 32 : 64)));
         ring_geometry(jt);
-        // the fast-FIR kernel where a thread has R = 8 outputs (D = 16); any complex64-aligned output: its epilogue picks the
-        // 16-byte store pairing per thread
-        if (fv == 7 || (fv == 0 && D == 16) || jt > 16) return ddch::launch_w(h, p, st, step, D, jt);
+        if (D == 16) return ddch::launch_w(h, p, st, step, D, jt);
         std::vector<float2> ctp((size_t)jt * D);
         make_ctaps(h, step, jt * D, ctp.data());
         return ddch::launch_pd(h, p, ctp.data(), st, D, jt);
@@ -1003,7 +1001,7 @@ int ddcb200_set_option(ddcb200_t* h, const char* key, int64_t value) {
         return DDCB200_OK;
     }
     if (!strcmp(key, "tc_ns")) {   // tuning: sub-streams of the tensor engine (0 = automatic)
-        if (value != 0 && value != 8 && value != 16 && value != 32) return fail(DDCB200_EINVAL, "tc_ns must be 0, 8, 16 or 32");
+        if (value != 0 && value != 8 && value != 16) return fail(DDCB200_EINVAL, "tc_ns must be 0, 8 or 16");
         h->tc_ns = (int)value;
         return DDCB200_OK;
     }

@@ -46,7 +46,6 @@ int launch_pd_j(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, int
 
 int launch_pd(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, int D, int jt) {
     switch (D) {
-        case 16: return launch_pd_j<16>(h, p, ct, st, jt);
         case 32: return launch_pd_j<32>(h, p, ct, st, jt);
         case 64: return launch_pd_j<64>(h, p, ct, st, jt);
     }

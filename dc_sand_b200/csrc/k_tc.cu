@@ -142,9 +142,6 @@ int launch_tc10_d(ddcb200* h, RunParams& p, const TcParams& tc, const TcGeom& g,
         case 16:
             if constexpr (D >= 8) return launch_tc10_t<D, 16>(h, p, tc, g.smem, st);
             break;
-        case 32:
-            if constexpr (D >= 16) return launch_tc10_t<D, 32>(h, p, tc, g.smem, st);
-            break;
     }
     return fail(DDCB200_EINVAL, "tensor engine: %d sub-streams at decimation %d are not built", g.NS, D);
 }

@@ -40,13 +40,11 @@ int launch_fused(ddcb200* h, RunParams& p, const float2* ctaps_host, cudaStream_
 
 template <int D, int R>
 int launch_fused_t(ddcb200* h, RunParams& p, const float2* ct, cudaStream_t st, int grid_limit, int ks) {
+    // one tap-parameter size (2048 complex taps = 16 KB of kernel parameters): the kernel is the fall-back for cells no other
+    // kernel takes, a second instantiation per (D, KS) for short filters is not worth its 8 entries
     if constexpr (R <= 4) {  // larger R: exchange buffer / register budget do not fit 544 threads
-        if (ks == 2) {
-            if (p.n_taps <= 512) return launch_fused<D, R, 2, 512>(h, p, ct, st, grid_limit);
-            return launch_fused<D, R, 2, kMaxTapsFused>(h, p, ct, st, grid_limit);
-        }
+        if (ks == 2) return launch_fused<D, R, 2, kMaxTapsFused>(h, p, ct, st, grid_limit);
     }
-    if (p.n_taps <= 512) return launch_fused<D, R, 1, 512>(h, p, ct, st, grid_limit);
     return launch_fused<D, R, 1, kMaxTapsFused>(h, p, ct, st, grid_limit);
 }
 }  // namespace

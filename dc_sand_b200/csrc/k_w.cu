@@ -51,9 +51,7 @@ int launch_w_j(ddcb200* h, RunParams& p, cudaStream_t st, double step, int jt) {
 
 int launch_w(ddcb200* h, RunParams& p, cudaStream_t st, double step, int D, int jt) {
     switch (D) {
-        case 16: return launch_w_j<16>(h, p, st, step, jt);
-        case 32: return launch_w_j<32>(h, p, st, step, jt);
-        case 64: return launch_w_j<64>(h, p, st, step, jt);
+        case 16: return launch_w_j<16>(h, p, st, step, jt);   // D = 32 / 64: the sliced kernel (k_ws*.cu) does the fast FIR there
     }
     return fail(DDCB200_EINVAL, "fast-FIR kernel: unsupported decimation %d", D);
 }

@@ -610,13 +610,14 @@ def test_randomised_dispatch_fuzz(tmp_path):
     assert len(seen) >= 5, seen
 
 
-@pytest.mark.parametrize("variant,name", [(7, "fused_fast_fir<"), (8, "deferred"), (11, "staged"), (2, "fused_tma")])
-def test_optional_kernel_variants_stay_correct(taps_dir, variant, name):
+@pytest.mark.parametrize("variant,name,dec", [(7, "fused_fast_fir<", 16), (8, "deferred", 32), (11, "staged", 16),
+                                              (2, "fused_tma", 16)])
+def test_optional_kernel_variants_stay_correct(taps_dir, variant, name, dec):
     """The alternative kernel families behind option `variant` keep producing reference results on the headline
-    filter (T = 256, D = 16)."""
+    filter (T = 256; D = 16, or 32 for the phase-major direct form, which is built for D = 32 / 64 only)."""
     n = (1 << 21) + 4 * 333
     xs = np.stack([synth.digitiser_stream_fast(n, 60 + s) for s in range(2)]).astype(np.float32)
-    ddc = _ddc(taps_dir, 16)
+    ddc = _ddc(taps_dir, dec)
     ddc.set_option("variant", variant)
     y = ddc.run_tensor(torch.from_numpy(xs).cuda(), 100e6).cpu().numpy()
     assert name in ddc.last_variant, ddc.last_variant
@@ -624,6 +625,6 @@ def test_optional_kernel_variants_stay_correct(taps_dir, variant, name):
     m = y.shape[1]
     scale = np.abs(y).max()
     for s in range(2):
-        for s0 in (0, 70_000, m - 512):
-            ref = orc.ddc_windowed_f64(xs[s], s0, 512, step, ddc.ddc_filter_coeffs, 16)
+        for s0 in (0, 35_000, m - 512):
+            ref = orc.ddc_windowed_f64(xs[s], s0, 512, step, ddc.ddc_filter_coeffs, dec)
             assert np.abs(y[s, s0:s0 + 512] - ref).max() <= TOL_MAX * scale, (variant, s, s0)
