@@ -16,6 +16,9 @@ from dc_sand_b200 import DigitalDownConverter, synth, taps  # noqa: E402
 from oracle import ddc_oracle as orc  # noqa: E402
 
 
+OPTIONS = []   # (key, value) pairs from --option, passed to ddcb200_set_option (e.g. tc_mode=1)
+
+
 def make_ddc(T, D, tmp):
     if T == 256 and D == 16:
         csv = taps.write_csv("ddc_coeff_107MHz.csv", tmp)
@@ -41,6 +44,8 @@ def one(T, D, n, streams, tmp, fc=100e6, full_range=False, verbose=True):
     m = ddc.out_len(n)
     out = torch.zeros((streams, m), dtype=torch.complex64, device="cuda")
     ddc.set_option("variant", 13)
+    for k, v in OPTIONS:
+        ddc.set_option(k, v)
     ddc.run_tensor(x, fc, out=out, packed=True)
     torch.cuda.synchronize()
     name = ddc.last_variant
@@ -71,7 +76,9 @@ def one(T, D, n, streams, tmp, fc=100e6, full_range=False, verbose=True):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", default="small")
+    ap.add_argument("--option", action="append", default=[], help="key=value passed to ddcb200_set_option")
     a = ap.parse_args()
+    OPTIONS.extend((kv.split("=")[0], int(kv.split("=")[1])) for kv in a.option)
     tmp = tempfile.mkdtemp()
     if a.cases == "small":
         one(256, 16, 8192 + 256, 1, tmp)
