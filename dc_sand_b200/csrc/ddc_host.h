@@ -79,7 +79,6 @@ struct ddcb200 {
     int tc_na = 0, tc_nraw = 0;            // options "tc_na" / "tc_nraw": force the A-stage / raw-slot counts (tuning)
     int tc_ns = 0, tc_ns_built = 0;        // option "tc_ns": force the sub-stream count (tuning); the one of the cached image
     int host_chunk_mode = 0;               // option "host_chunk_mode": 0 by-stream chunks for batches of short streams, 1 time chunks
-    int tc_mode = 0;                       // option "tc_mode": 0 automatic, 1 samples as the A operand (ddc_kernel_tc.cuh), 2 taps in tensor memory (ddc_kernel_tct.cuh)
     int packed_engine = 1;                 // option "packed_engine": 1 tensor cores where supported (default), 0 CUDA cores
     ddcb200_c64* h_ostage[kBufs] = {};   // pinned landing buffers for the complex128 host path (one per chunk buffer)
     size_t ostage_cap = 0;

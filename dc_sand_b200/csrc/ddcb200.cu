@@ -1000,11 +1000,6 @@ int ddcb200_set_option(ddcb200_t* h, const char* key, int64_t value) {
         h->packed_engine = (int)value;
         return DDCB200_OK;
     }
-    if (!strcmp(key, "tc_mode")) {   // form of the tensor engine: 0 automatic, 1 samples as A operand, 2 tap matrix in tensor memory
-        if (value < 0 || value > 2) return fail(DDCB200_EINVAL, "tc_mode must be 0, 1 or 2");
-        h->tc_mode = (int)value;
-        return DDCB200_OK;
-    }
     if (!strcmp(key, "tc_ns")) {   // tuning: sub-streams of the tensor engine (0 = automatic)
         if (value != 0 && value != 8 && value != 16) return fail(DDCB200_EINVAL, "tc_ns must be 0, 8 or 16");
         h->tc_ns = (int)value;

@@ -10,7 +10,6 @@
 
 #include "ddc_host.h"
 #include "ddc_kernel_tc.cuh"
-#include "ddc_kernel_tct.cuh"
 
 using namespace ddck;
 
@@ -120,112 +119,6 @@ void build_b(const ddcb200* h, double step, const TcGeom& g, __half* out, float*
         }
 }
 
-// ---- second form (ddc_kernel_tct.cuh): tap matrix in tensor memory, R = 32 outputs per sample row ------------------------------
-// NR = 64 sample rows per tile (the MMA's N: an MMA costs the fetch of its 128-row A slice whatever N is, so N = 32 leaves the
-// tensor pipe fetch-bound); 2 NR accumulator columns + K / 2 columns of taps must fit the 512 columns of tensor memory, which
-// bounds the filter length (D = 16: T <= 272; D = 8: T <= 520)
-TcGeom tct_geometry(int T, int D, int force_na = 0, int force_nraw = 0) {
-    TcGeom g{};
-    g.D = D;
-    g.T = T;
-    g.ok = false;
-    if (D != 16 && D != 8) return g;
-    g.R = 32;
-    g.row_s = g.R * D;
-    g.NS = g.row_s / 8;
-    g.N = 64;                                                 // NR: sample rows per tile (two raw chunks at D = 16, one at D = 8)
-    g.tile_s = g.N * g.row_s;
-    g.K = (g.row_s - D + T + 15) / 16 * 16;
-    g.k16 = g.K / 16;
-    if (2 * g.N + g.K / 2 > 512 || T < 1) return g;           // TctShape::ACC_COLS + tap columns
-    const int n_chunk = g.tile_s / 16384;
-    g.n_groups = (16384 + g.K - g.row_s) / 16;                // 16-sample groups of one raw chunk, halo included
-    g.a_rows = (2 * ((n_chunk - 1) * 1024 + g.n_groups) + g.NS - 1) / g.NS;
-    g.a_pitch = 16 * (g.a_rows | 1);
-    g.a_stage = (g.NS * g.a_pitch + 127) & ~127;
-    g.raw_bytes = (20 * g.n_groups + 15) & ~15;
-    g.raw_slot = (g.raw_bytes + 127) & ~127;
-    g.b_bytes = g.K * 128 * 2;                                // image [K / 16][128][8 words]
-    if (g.n_groups > TcShape<8>::UNP_BATCH * 32 * TcShape<8>::NUNP) return g;
-    const size_t cap = 227 * 1024, fixed = 1024;
-    int na = force_na ? force_na : 3;
-    while (!force_na && na > 2 && fixed + (size_t)na * g.a_stage + 4 * (size_t)g.raw_slot > cap) --na;   // keep four raw slots
-    if (fixed + (size_t)na * g.a_stage + 2 * (size_t)g.raw_slot > cap) return g;
-    int nr = (int)((cap - fixed - (size_t)na * g.a_stage) / (size_t)g.raw_slot);
-    nr = std::min(nr, 8);
-    if (force_nraw) nr = std::min(nr, force_nraw);
-    g.n_a = na;
-    g.n_raw = nr;
-    g.smem = fixed + (size_t)na * g.a_stage + (size_t)nr * g.raw_slot;
-    g.ok = nr >= 2 && g.smem / 16 < (1u << 14) && g.a_pitch / 16 < (1 << 13);
-    return g;
-}
-
-// A[(r, c), k] = part c of S * tap(k - D r) * e^{-j 2 pi step k} (the same values as build_b), row m = 32 (r / 8) + 8 c + r % 8,
-// image [K / 16][128][16] halves: what one lane writes to its tensor-memory row per K-step is 32 contiguous bytes
-void build_a(const ddcb200* h, double step, const TcGeom& g, __half* out, float* inv_scale, float* lo_scale) {
-    const int T = g.T;
-    std::vector<double> rc(g.K), rs(g.K);
-    const double fstep = step - std::floor(step);
-    for (int k = 0; k < g.K; ++k) {
-        double ph = fstep * (double)k;
-        ph -= std::floor(ph);
-        rc[k] = std::cos(-2.0 * M_PI * ph);
-        rs[k] = std::sin(-2.0 * M_PI * ph);
-    }
-    double hmax = 0.0;
-    for (int t = 0; t < T; ++t) hmax = std::max(hmax, std::fabs(h->taps[t] / h->taps_sum));
-    int e = 0;
-    if (hmax > 0.0) e = (int)std::floor(std::log2(32768.0 / hmax));
-    if (std::ldexp(hmax, e) >= 32768.0) --e;
-    e = std::max(-14, std::min(e, 40));
-    const double S = std::ldexp(1.0, e);
-    *inv_scale = (float)(512.0 / S);
-    *lo_scale = (float)(512.0 / (2048.0 * S));
-    std::memset(out, 0, (size_t)g.b_bytes);
-    auto split = [&](double v, __half& hi, __half& lo) {
-        hi = __float2half_rn((float)(v * S));
-        const double res = v * S - (double)__half2float(hi);
-        lo = __float2half_rn((float)(res * 2048.0));
-    };
-    for (int r = 0; r < g.R; ++r)
-        for (int t = 0; t < T; ++t) {
-            const int k = t + g.D * r;
-            const double hk = h->taps[T - 1 - t] / h->taps_sum;
-            __half* row0 = out + ((size_t)(k / 16) * 128 + 32 * (r / 8) + (r % 8)) * 16 + (k % 16);   // part c: + 8 c rows
-            __half hi, lo;
-            split(hk * rc[k], hi, lo);
-            row0[0 * 8 * 16] = hi;
-            row0[1 * 8 * 16] = lo;
-            split(hk * rs[k], hi, lo);
-            row0[2 * 8 * 16] = hi;
-            row0[3 * 8 * 16] = lo;
-        }
-}
-
-template <int D, int NR>
-int launch_tc10t_t(ddcb200* h, RunParams& p, const TcParams& tc, size_t smem, cudaStream_t st) {
-    auto kern = ddc_tc10t_kernel<D, NR>;
-    static bool attr_set[64] = {};
-    if (h->device < 64 && !attr_set[h->device]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set[h->device] = true;
-    }
-    const long long grid = std::min<long long>(p.total_tiles, h->sm_count);
-    kern<<<(unsigned)grid, TctShape<D, NR>::NTHREADS, smem, st>>>(p, tc);
-    CUDA_TRY(cudaGetLastError());
-    return DDCB200_OK;
-}
-
-// which form runs a (T, D): the second only on request (option "tc_mode" = 2) -- measured equal on BASELINE configs[2] and
-// within +-5 % in the sweep cells it fits (profiles/r2_tensor_engine_taps_in_tmem.md)
-bool tct_selected(const ddcb200* h, int T, int D, TcGeom* out) {
-    if (!h || h->tc_mode != 2 || h->tc_ns) return false;
-    const TcGeom g = tct_geometry(T, D, h ? h->tc_na : 0, h ? h->tc_nraw : 0);
-    if (out) *out = g;
-    return g.ok;
-}
-
 template <int D, int NS>
 int launch_tc10_t(ddcb200* h, RunParams& p, const TcParams& tc, size_t smem, cudaStream_t st) {
     auto kern = ddc_tc10_kernel<D, NS>;
@@ -255,21 +148,17 @@ int launch_tc10_d(ddcb200* h, RunParams& p, const TcParams& tc, const TcGeom& g,
 
 bool tc10_supported(const ddcb200* h, int T, int D) {
     if (!(D == 4 || D == 8 || D == 16 || D == 32 || D == 64) || T < 1) return false;
-    if (tct_selected(h, T, D, nullptr)) return true;
-    if (h && h->tc_mode == 2) return false;
     return tc_pick(h, T, D).ok;
 }
 
 int launch_tc10(ddcb200* h, RunParams& p, cudaStream_t st, double step, int D) {
     const int T = (int)h->taps.size();
-    TcGeom g{};
-    const bool second = tct_selected(h, T, D, &g);   // tap matrix in tensor memory (ddc_kernel_tct.cuh)
-    if (!second) g = tc_pick(h, T, D);
+    const TcGeom g = tc_pick(h, T, D);
     if (!g.ok) return fail(DDCB200_EINVAL, "tensor engine: %d taps at decimation %d do not fit shared memory", T, D);
 
     // ---- B operand: cached while (step, D, taps) repeat; a ring of device images so that a new key never overwrites one that
     // a queued kernel still reads
-    const bool hit = h->tc_slot >= 0 && h->tc_step == step && h->tc_d == D && h->tc_ns_built == (second ? -g.NS : g.NS) && h->tc_version == h->taps_version;
+    const bool hit = h->tc_slot >= 0 && h->tc_step == step && h->tc_d == D && h->tc_ns_built == g.NS && h->tc_version == h->taps_version;
     if (!hit) {
         const int slot = (h->tc_slot + 1) % ddcb200::kTcRing;
         if (h->tc_ev[slot]) CUDA_TRY(cudaEventSynchronize(h->tc_ev[slot]));   // the last kernel that read this image is done
@@ -285,14 +174,13 @@ int launch_tc10(ddcb200* h, RunParams& p, cudaStream_t st, double step, int D) {
             CUDA_TRY(cudaMallocHost(&h->h_tc_b[slot], cap));
             h->tc_cap[slot] = cap;
         }
-        if (second) build_a(h, step, g, static_cast<__half*>(h->h_tc_b[slot]), &h->tc_inv_scale, &h->tc_lo_scale);
-        else build_b(h, step, g, static_cast<__half*>(h->h_tc_b[slot]), &h->tc_inv_scale, &h->tc_lo_scale);
+        build_b(h, step, g, static_cast<__half*>(h->h_tc_b[slot]), &h->tc_inv_scale, &h->tc_lo_scale);
         CUDA_TRY(cudaMemcpyAsync(h->d_tc_b[slot], h->h_tc_b[slot], (size_t)g.b_bytes, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaEventRecord(h->tc_up_ev, st));
         h->tc_slot = slot;
         h->tc_step = step;
         h->tc_d = D;
-        h->tc_ns_built = second ? -g.NS : g.NS;
+        h->tc_ns_built = g.NS;
         h->tc_version = h->taps_version;
     } else {
         CUDA_TRY(cudaStreamWaitEvent(st, h->tc_up_ev, 0));   // the image may have been uploaded on another stream
@@ -315,7 +203,7 @@ int launch_tc10(ddcb200* h, RunParams& p, cudaStream_t st, double step, int D) {
     tc.unp_mul[0] = 1u << 10;
     tc.unp_mul[1] = 1u << 14;
 
-    const long long tile_out = second ? (long long)g.N * g.R : 128LL * g.R;
+    const long long tile_out = 128LL * g.R;
     p.tiles_per_stream = (p.n_out + tile_out - 1) / tile_out;
     p.total_tiles = p.tiles_per_stream * p.n_streams;
     p.n_taps = T;
@@ -323,16 +211,6 @@ int launch_tc10(ddcb200* h, RunParams& p, cudaStream_t st, double step, int D) {
     p.m_begin = 0;
 
     int rc = DDCB200_OK;
-    if (second) {
-        rc = D == 16 ? launch_tc10t_t<16, 64>(h, p, tc, g.smem, st) : launch_tc10t_t<8, 64>(h, p, tc, g.smem, st);
-        if (rc) return rc;
-        CUDA_TRY(cudaEventRecord(h->tc_ev[h->tc_slot], st));
-        h->launches++;
-        char name2[128];
-        snprintf(name2, sizeof(name2), "tensor_fir_packed10_taps_in_tmem<D%d,ROW%d,M128,N%d,K%d,S%d,RAW%d>", D, g.row_s, g.N, g.K, g.n_a, g.n_raw);
-        h->last_variant = name2;
-        return DDCB200_OK;
-    }
     switch (D) {
         case 4: rc = launch_tc10_d<4>(h, p, tc, g, st); break;
         case 8: rc = launch_tc10_d<8>(h, p, tc, g, st); break;

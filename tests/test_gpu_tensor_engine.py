@@ -63,35 +63,6 @@ def test_tensor_engine_full_code_range(d, t, tmp_path):
         assert yp[s].shape == ref.shape and emax <= k * TOL_MAX and el2 <= k * TOL_L2, (s, ddc.last_variant, emax, el2)
 
 
-@pytest.mark.parametrize("d,t,n", [(16, 256, 5 * 16384 + 64), (16, 256, 32768), (16, 272, 70016), (16, 2, 40000 // 64 * 64), (8, 128, 3 * 16384 + 4416),
-                                   (8, 512, 50048), (8, 520, 16384)])
-def test_tensor_engine_both_forms_agree(d, t, n, tmp_path):
-    """The two forms of the engine -- samples as the A operand (ddc_kernel_tc.cuh, option tc_mode = 1) and the tap matrix in
-    tensor memory (ddc_kernel_tct.cuh, tc_mode = 2, the default where the taps fit 512 columns) -- on full-range codes: each
-    against the reference arithmetic, and against each other.  Lengths: several tiles with a ragged last one, exactly one tile
-    of the second form, one raw chunk."""
-    xs = _full_range_streams(n)
-    tp = _taps_for(t, d) if t > 3 else np.ones(t)
-    ddc = DigitalDownConverter(d, FS, _custom_taps(tmp_path, tp))
-    ys = {}
-    for mode, name in ((1, "tensor_fir_packed10<"), (2, "tensor_fir_packed10_taps_in_tmem<")):
-        ddc.set_option("tc_mode", mode)
-        ys[mode] = _run_packed(ddc, xs).cpu().numpy()
-        assert name in ddc.last_variant, (mode, ddc.last_variant)
-    k = 4 if t > 256 else 1
-    for s in range(xs.shape[0]):
-        ref = orc.ddc_reference(xs[s].astype(np.float32), 100e6, tp, d, FS)
-        for mode in (1, 2):
-            emax, el2 = rel_err(ys[mode][s], ref)
-            assert ys[mode][s].shape == ref.shape and emax <= k * TOL_MAX and el2 <= k * TOL_L2, (mode, s, emax, el2)
-    assert np.abs(ys[1] - ys[2]).max() <= k * TOL_MAX * np.abs(ys[1]).max()
-    ddc.set_option("tc_mode", 2)
-    ddc.decimation_factor = 64                      # the second form is built for D = 8 / 16: forcing it elsewhere leaves the CUDA cores
-    _run_packed(ddc, xs[:, : n // 64 * 64])
-    assert "tensor_fir" not in ddc.last_variant, ddc.last_variant
-    ddc.close()
-
-
 @pytest.mark.parametrize("d", [8, 16, 64])
 def test_tensor_engine_unpack_is_bit_exact(d, tmp_path):
     """Impulse-response form of "bit-exact unpack": one tap equal to 1, all others 0, and a centre frequency that makes the
