@@ -7,10 +7,12 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "ddc_common.cuh"
+#include "host_pool.h"
 
 namespace ddch {
 int fail(int code, const char* fmt, ...);   // records the thread-local message of ddcb200_last_error() and returns `code`
@@ -56,12 +58,13 @@ struct ddcb200 {
     double wt_step = 0.0;
     int wt_jt = 0, wt_d = 0;
     // pinned staging for pageable host input (see staged_h2d)
-    static constexpr int kStage = 2;
+    static constexpr int kStage = 3;
     static constexpr size_t kStageBytes = 8u << 20;
     void* h_stage[kStage] = {};
     cudaEvent_t ev_stage[kStage] = {};
     int stage_pos = 0;
-    int copy_threads = 4;
+    int copy_threads = 8;                  // option "copy_threads": host threads of the staging / widening (capped by the machine's cores)
+    std::unique_ptr<ddch::HostPool> pool;  // copy_threads - 1 parked workers (host_pool.h), created on first use
     float* d_unpack_ws = nullptr;          // float32 workspace of the two-launch packed path (unpack, then a float32 kernel)
     size_t unpack_ws_cap = 0;
     cudaEvent_t unpack_ev = nullptr;       // end of the last kernel that read the workspace (calls may come on different streams)

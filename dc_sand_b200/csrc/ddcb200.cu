@@ -475,12 +475,20 @@ bool is_pageable(const void* p) {
     return a.type == cudaMemoryTypeUnregistered;
 }
 
+// the handle's parked host threads (host_pool.h): copy_threads - 1 workers, never more than the machine has cores to spare
+ddch::HostPool& host_pool(ddcb200* h) {
+    const int hw = (int)std::thread::hardware_concurrency();
+    const int want = std::max(0, std::min({h->copy_threads, 16, hw > 1 ? hw - 1 : 1}) - 1);
+    if (!h->pool || h->pool->workers() != want) h->pool.reset(new ddch::HostPool(want));
+    return *h->pool;
+}
+
 int staged_h2d(ddcb200* h, void* d_dst, const void* h_src, size_t bytes, cudaStream_t st) {
     for (int i = 0; i < ddcb200::kStage; ++i) {
         if (!h->h_stage[i]) CUDA_TRY(cudaMallocHost(&h->h_stage[i], ddcb200::kStageBytes));
         if (!h->ev_stage[i]) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_stage[i], cudaEventDisableTiming));
     }
-    const int nt = std::max(1, std::min(h->copy_threads, 16));
+    ddch::HostPool& pool = host_pool(h);
     size_t done = 0;
     while (done < bytes) {
         const size_t n = std::min(bytes - done, ddcb200::kStageBytes);
@@ -489,17 +497,12 @@ int staged_h2d(ddcb200* h, void* d_dst, const void* h_src, size_t bytes, cudaStr
         CUDA_TRY(cudaEventSynchronize(h->ev_stage[b]));   // the copy engine has drained this staging buffer
         char* dst = static_cast<char*>(h->h_stage[b]);
         const char* src = static_cast<const char*>(h_src) + done;
-        if (nt == 1 || n < (1u << 20)) {
+        if (n < (1u << 20)) {
             std::memcpy(dst, src, n);
         } else {
-            const size_t per = ((n + nt - 1) / nt + 63) & ~(size_t)63;
-            std::vector<std::thread> th;
-            for (int t = 1; t < nt; ++t) {
-                const size_t o = per * t;
-                if (o < n) th.emplace_back([=] { std::memcpy(dst + o, src + o, std::min(per, n - o)); });
-            }
-            std::memcpy(dst, src, std::min(per, n));
-            for (auto& t : th) t.join();
+            const size_t per = 512u << 10;   // pieces of 512 KB: enough of them that a late worker does not set the pace
+            const int parts = (int)((n + per - 1) / per);
+            pool.run(parts, [=](int i) { std::memcpy(dst + per * i, src + per * i, std::min(per, n - per * i)); });
         }
         CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(d_dst) + done, dst, n, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaEventRecord(h->ev_stage[b], st));
@@ -508,26 +511,21 @@ int staged_h2d(ddcb200* h, void* d_dst, const void* h_src, size_t bytes, cudaStr
     return DDCB200_OK;
 }
 
-// complex64 -> complex128 on a few host threads, straight into the caller's (usually fresh, untouched) array: the page
+// complex64 -> complex128 on the host threads, straight into the caller's (usually fresh, untouched) array: the page
 // faults of the first touch are spread over the threads as well
-void widen_c64_to_c128(const ddcb200_c64* src, double* dst, size_t n, int nt) {
+void widen_c64_to_c128(ddcb200* h, const ddcb200_c64* src, double* dst, size_t n) {
     auto work = [=](size_t a, size_t b) {
         for (size_t i = a; i < b; ++i) {
             dst[2 * i] = (double)src[i].re;
             dst[2 * i + 1] = (double)src[i].im;
         }
     };
-    nt = std::max(1, std::min(nt, 16));
-    if (nt == 1 || n < (1u << 16)) {
+    if (!h || n < (1u << 16)) {
         work(0, n);
         return;
     }
-    const size_t per = (n + nt - 1) / nt;
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; ++t)
-        if (per * t < n) th.emplace_back(work, per * t, std::min(n, per * (t + 1)));
-    work(0, std::min(per, n));
-    for (auto& t : th) t.join();
+    const size_t per = 1u << 15;
+    host_pool(h).run((int)((n + per - 1) / per), [=](int i) { work(per * i, std::min(n, per * (i + 1))); });
 }
 
 // Host path: every stream is cut into time chunks of `chunk_samples` (+ T-D halo); chunk c of all streams goes
@@ -580,7 +578,7 @@ int run_host(ddcb200* h, const void* h_in, bool packed, int64_t n_samples, int64
     auto flush_pending = [&]() -> int {
         if (pend_m0 < 0) return DDCB200_OK;
         CUDA_TRY(cudaEventSynchronize(h->ev_out[pend_b]));
-        widen_c64_to_c128(h->h_ostage[pend_b], h_out128 + 2 * pend_m0, (size_t)pend_mc, std::max(1, h->copy_threads));
+        widen_c64_to_c128(h, h->h_ostage[pend_b], h_out128 + 2 * pend_m0, (size_t)pend_mc);
         pend_m0 = -1;
         return DDCB200_OK;
     };
@@ -930,7 +928,7 @@ int ddcb200_run_host_f32_c128(ddcb200_t* h, const float* h_in, int64_t n_samples
         std::vector<ddcb200_c64> tmp((size_t)m);
         int rc = ddcb200_run_host_f32(h, h_in, n_samples, 1, n_samples, step, sample_offset, tmp.data(), m);
         if (rc) return rc;
-        widen_c64_to_c128(tmp.data(), h_out, (size_t)m, 1);
+        widen_c64_to_c128(nullptr, tmp.data(), h_out, (size_t)m);
         return DDCB200_OK;
     }
     return run_host(h, h_in, false, n_samples, 1, n_samples, step, sample_offset, nullptr, 0, h_out);
