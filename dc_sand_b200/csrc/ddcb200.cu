@@ -237,7 +237,7 @@ static inline bool aligned_f32(const void* d_in, int64_t in_stride, bool packed)
 }
 
 // Core dispatcher for device-resident data.  Option "variant" (ddcb200_set_option): 0 auto; 1 generic kernel; 2 / 3 tile kernel
-// without / with the tap split; 7 fast FIR (ddc_kernel_w.cuh, also for D = 32 / 64); 8 phase-major direct form; 10 warp-
+// without / with the tap split; 7 fast FIR (ddc_kernel_w.cuh, D = 16); 8 phase-major direct form (D = 32 / 64); 10 warp-
 // specialised CUDA-core packed kernel; 11 tensor-staged / sliced fast FIR; 13 tensor-core engine for packed input.
 int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int64_t n_streams, int64_t in_stride,
                double step, int64_t sample_offset, ddcb200_c64* d_out, int64_t out_stride, cudaStream_t st,

@@ -181,12 +181,14 @@ int64_t ddcb200_launch_count(ddcb200_t* handle);
 /* Name of the kernel variant the last run on this handle dispatched to (e.g. "fused_tma<D16,R4,T256>"). */
 const char* ddcb200_last_variant(ddcb200_t* handle);
 /* Tuning/diagnostic knobs (all optional; 0 restores the default):
- *   "variant"        kernel choice: 0 auto, 1 generic, 2 / 3 tile kernel without / with the tap split, 5 direct-form packed
- *                    kernel, 7 fast FIR on 1-D bulk copies, 8 phase-major direct form, 10 warp-specialised packed kernel,
- *                    11 tensor-staged / sliced fast FIR (see DESIGN.md section 4 and tools/README.md);
+ *   "variant"        kernel choice: 0 auto, 1 generic, 2 / 3 tile kernel without / with the tap split, 7 fast FIR on 1-D bulk
+ *                    copies (D = 16), 8 phase-major direct form (D = 32 / 64), 10 warp-specialised CUDA-core packed kernel,
+ *                    11 tensor-staged / sliced fast FIR, 13 tensor-core engine for packed input (see DESIGN.md section 4
+ *                    and tools/README.md); a choice that is not built for the call's (taps, decimation) falls through to auto;
  *   "chunk_samples"  time-chunk size of the host path (default 2^24 samples per launch);
- *   "copy_threads"   host threads that stage pageable input through pinned buffers and widen complex128 output (default 4,
- *                    0 = leave pageable copies to the driver);
+ *   "copy_threads"   host threads that stage pageable input through pinned buffers and widen complex128 output (a pool
+ *                    parked in the handle; default 8, never more than the machine's cores; 0 = leave pageable copies to the
+ *                    driver);
  *   "packed_engine"  engine for packed 10-bit input: 1 (default) the tcgen05 tensor-core engine wherever it applies
  *                    (decimation 4 .. 64 a power of two, 16-byte aligned rows, filter fits shared memory), 0 the CUDA-core
  *                    kernels; float32 input always runs on the CUDA cores;
