@@ -52,16 +52,17 @@ def measured_peaks():
 
 def ncu_traffic(workload: str, variant: str):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the committed
-    `ncu --set full` capture of this workload (profiles/ncu_traffic.json); None if the capture is of another kernel."""
+    `ncu --set full` capture of this workload (profiles/ncu_traffic.json), with the capture it comes from; (None, None) if
+    the capture is of another kernel."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         with open(p) as f:
             rec = json.load(f).get(workload)
     except (OSError, ValueError):
-        return None
+        return None, None
     if not rec or not variant.startswith(rec.get("variant_prefix", "\0")):
-        return None
-    return rec.get("dram_bytes_per_launch")
+        return None, None
+    return rec.get("dram_bytes_per_launch"), rec.get("source")
 
 
 class ClockSampler:
@@ -269,7 +270,7 @@ def workload_name(args):
 # ----------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------
-def roofline_of(n_streams, n, m, t, d, packed, kern_s, variant, hbm_peak, peak_src, traffic=None):
+def roofline_of(n_streams, n, m, t, d, packed, kern_s, variant, hbm_peak, peak_src, traffic=(None, None)):
     """algorithmic bytes = (B_in + 8 / D) per input sample, direct-form flops = 4 T per output; the fast-FIR
     kernels EXECUTE 3/4 of those multiplies (plus one packed subtraction per window sample, not counted).  `bound` is the
     floor that binds: max(bytes / HBM peak, executed flops / CUDA-core FP32 peak); `floor_frac` = t_floor / t."""
@@ -294,7 +295,8 @@ def roofline_of(n_streams, n, m, t, d, packed, kern_s, variant, hbm_peak, peak_s
         "peak": hbm_peak,
         "unit": "GB/s",
         "frac": achieved / hbm_peak,
-        "traffic": traffic,
+        "traffic": traffic[0],
+        "traffic_source": traffic[1],
         "peak_source": peak_src,
         "frac_of_nominal_8TBs": achieved / 8000.0,
         "floor_frac": max(t_hbm, t_fp32) / kern_s,
