@@ -236,9 +236,70 @@ static inline bool aligned_f32(const void* d_in, int64_t in_stride, bool packed)
     return !packed && (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (in_stride % 4 == 0);
 }
 
-// Core dispatcher for device-resident data.  Option "variant" (ddcb200_set_option): 0 auto; 1 generic kernel; 2 / 3 tile kernel
-// without / with the tap split; 7 fast FIR (ddc_kernel_w.cuh, D = 16); 8 phase-major direct form (D = 32 / 64); 10 warp-
-// specialised CUDA-core packed kernel; 11 tensor-staged / sliced fast FIR; 13 tensor-core engine for packed input.
+// ---------------------------------------------------------------------------------------------------------------------
+// Kernel selection: a PURE function of the call's shape and the handle's options (exported as ddcb200_plan so that the
+// selection table is testable without a GPU).  Rules in order; the first that applies wins:
+//   1  packed, 16-byte aligned rows, D a power of two 4 .. 64, filter fits       -> tensor-core engine (ddc_kernel_tc.cuh)
+//   2  packed, aligned, D = 16, 129 .. 256 taps, packed_engine = 0 / variant 10  -> warp-specialised CUDA-core kernel (ddc_kernel_w10.cuh)
+//   3  packed otherwise (variant != 1)                                           -> unpack stage + the float32 plan of the cell
+//   4  float32, aligned, tensor-staged / sliced fast FIR (ddc_kernel_ws.cuh):
+//        D = 4 / 8 up to 1024 taps where its tap padding costs <= 12 % over the tile kernel's, D = 16 up to 128 taps,
+//        D = 32 / 64 where the direct form is FP32-bound (4 T / D flop against 4 + 8 / D bytes at the ridge of 11.4 flop/B)
+//   5  float32, aligned, ring kernels on 1-D bulk copies: D = 16 up to 64 tap blocks -> fast FIR (ddc_kernel_w.cuh);
+//        D = 32 / 64 up to 16 tap blocks -> phase-major direct form (ddc_kernel_p.cuh)
+//   6  float32, aligned, D a power of two, padded filter <= 2048 taps            -> rotating-window tile kernel
+//   7  everything else (odd decimations, unaligned rows, > 2048 taps, variant 1) -> generic kernel
+// `skip` excludes families a caller has found inapplicable at run time (tile counts beyond an index range, inputs shorter
+// than one thread-row).  Measurements behind the thresholds: DESIGN.md section 4.
+// ---------------------------------------------------------------------------------------------------------------------
+enum KernelFamily { KF_TENSOR10 = 0, KF_W10S, KF_UNPACK_F32, KF_WS, KF_W, KF_PD, KF_TILE, KF_GENERIC, KF_COUNT };
+const char* const kFamilyName[KF_COUNT] = {"tensor10", "w10s", "unpack+f32", "ws", "w", "pd", "tile", "generic"};
+
+struct KernelPlan {
+    KernelFamily family;
+    int jt;   // tap blocks the launcher is instantiated for (WS / W / PD), padded blocks of the tile kernel
+    int ks;   // tile kernel: warps that share a tap split
+};
+
+KernelPlan plan_kernel(int T, int D, bool packed, bool aligned, int fv, int packed_engine, bool tensor_ok, unsigned skip = 0) {
+    const int Jp = (T + D - 1) / D;   // tap blocks of D taps
+    const bool pow2_d = D == 4 || D == 8 || D == 16 || D == 32 || D == 64;
+    auto allowed = [&](KernelFamily f) { return !(skip & (1u << f)); };
+    if (packed) {
+        if (aligned && pow2_d && tensor_ok && (fv == 13 || (fv == 0 && packed_engine == 1)) && allowed(KF_TENSOR10)) return {KF_TENSOR10, 0, 0};
+        if (aligned && D == 16 && Jp > 8 && Jp <= 16 && (fv == 0 || fv == 10)) return {KF_W10S, 16, 0};
+        if (fv != 1) return {KF_UNPACK_F32, 0, 0};
+        return {KF_GENERIC, 0, 0};
+    }
+    if (aligned && pow2_d && fv != 1 && allowed(KF_WS)) {
+        const int r_tile = 64 / D;   // outputs per thread of the tile kernel
+        const bool fp32_bound = 4.0 * T / D > 11.4 * (4.0 + 8.0 / D);
+        const int jt_ws = Jp <= 8 ? 8 : (Jp <= 64 ? (Jp + 15) / 16 * 16 : (Jp + 31) / 32 * 32);   // the instantiations of k_ws.inc
+        const int j_tile = (Jp + r_tile - 1) / r_tile * r_tile;
+        const bool pad_ok = jt_ws * 100 <= j_tile * 112;
+        const bool auto_ws = ((D == 4 || D == 8) && T <= 1024 && pad_ok) || (D == 16 && T <= 128) || ((D == 32 || D == 64) && fp32_bound);
+        if (Jp <= (D == 4 ? 256 : (D == 8 ? 128 : 32)) && T >= D && (fv == 11 || (fv == 0 && auto_ws))) return {KF_WS, jt_ws, 0};
+    }
+    if (aligned && ((D == 16 && Jp <= 64) || ((D == 32 || D == 64) && Jp <= 16)) && (fv == 0 || fv == 7 || fv == 8)) {
+        const int jt = Jp <= 4 ? 4 : (Jp <= 8 ? 8 : (Jp <= 16 ? 16 : (Jp <= 32 ? 32 : 64)));
+        return {D == 16 ? KF_W : KF_PD, jt, 0};
+    }
+    if (aligned && pow2_d && fv != 1) {
+        const int R = 64 / D;
+        // tap split 2 (16 compute warps) whenever it costs no extra zero taps; option "variant" 2 / 3 force KS 1 / 2
+        int ks = (Jp % (2 * R) == 0 && R <= 4) ? 2 : 1;
+        if (fv == 2) ks = 1;
+        if (fv == 3 && R <= 4) ks = 2;
+        const int J = ((Jp + ks * R - 1) / (ks * R)) * (ks * R);   // each thread's tap-block loop is unrolled R times
+        if (J * D <= 2048) return {KF_TILE, J, ks};
+    }
+    return {KF_GENERIC, 0, 0};
+}
+
+// Core dispatcher for device-resident data: plan_kernel() picks the family, this function sizes the launch.  Option "variant"
+// (ddcb200_set_option): 0 auto; 1 generic kernel; 2 / 3 tile kernel without / with the tap split; 7 fast FIR (ddc_kernel_w.cuh,
+// D = 16); 8 phase-major direct form (D = 32 / 64); 10 warp-specialised CUDA-core packed kernel; 11 tensor-staged / sliced fast
+// FIR; 13 tensor-core engine for packed input; a choice that is not built for the call's (taps, decimation) falls through.
 int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int64_t n_streams, int64_t in_stride,
                double step, int64_t sample_offset, ddcb200_c64* d_out, int64_t out_stride, cudaStream_t st,
                int64_t m_limit = -1) {
@@ -270,8 +331,6 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
     p.l2_ahead = h->l2_ahead;
     p.dbg = h->d_dbg;
 
-    const int Jp = (T + D - 1) / D;   // tap blocks of D taps
-    const bool pow2_d = D == 4 || D == 8 || D == 16 || D == 32 || D == 64;
     // ring kernels (ddc_kernel_p / _w / _w10.cuh): chunks of 32 thread-rows of 128 samples
     auto ring_geometry = [&](int jt) {
         const long long chunk_out = 32LL * (128 / D);
@@ -282,23 +341,21 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         p.m_begin = 0;
     };
 
-    // ---- packed 10-bit input on the tensor cores (default engine for packed input; option "packed_engine" = 0 or a CUDA-core
-    // "variant" selects the kernels below; "variant" = 13 forces it; ddc_kernel_tc.cuh) ---
-    if (packed && (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (in_stride % 16 == 0) && pow2_d &&
-        (fv == 13 || (fv == 0 && h->packed_engine == 1)) && ddch::tc10_supported(h, T, D) &&
-        (double)((M + 127) / 128) * (double)n_streams < 2.0e9)
-        return ddch::launch_tc10(h, p, st, step, D);
+    const bool aligned = packed ? (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (in_stride % 16 == 0) : aligned_f32(d_in, in_stride, packed);
+    const bool tensor_ok = packed && ddch::tc10_supported(h, T, D) && (double)((M + 127) / 128) * (double)n_streams < 2.0e9;
+    KernelPlan plan = plan_kernel(T, D, packed, aligned, fv, h->packed_engine, tensor_ok);
+    long long m_done = 0;        // outputs [0, m_done) of every stream are written by the fused kernel of the plan
+    bool fused_done = false;
 
-    // ---- packed 10-bit input on the CUDA cores (option packed_engine = 0): warp-specialised fast-FIR kernel with the unpack fused
-    // behind the TMA ring where it is instantiated (D = 16, 129 .. 256 taps: 1.10 ms on 64 x 2^24 samples) -------------------------
-    if (packed && (reinterpret_cast<uintptr_t>(d_in) % 16 == 0) && (in_stride % 16 == 0) && D == 16 && Jp > 8 && Jp <= 16 &&
-        (fv == 0 || fv == 10)) {
-        ring_geometry(16);
+    if (plan.family == KF_TENSOR10) return ddch::launch_tc10(h, p, st, step, D);
+
+    if (plan.family == KF_W10S) {
+        ring_geometry(plan.jt);
         return ddch::launch_w10s(h, p, st, step);
     }
 
-    // ---- packed input without a fused-unpack kernel for this (T, D): unpack into a float32 workspace, then the float32 path --
-    if (packed && fv != 1) {
+    if (plan.family == KF_UNPACK_F32) {
+        // packed input without a fused-unpack kernel for this (T, D): unpack into a float32 workspace, then the float32 plan
         const long long pitch = (n_samples + 3) / 4 * 4;
         const size_t need = (size_t)pitch * (size_t)n_streams;
         if (need > h->unpack_ws_cap) {
@@ -329,86 +386,55 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
         return DDCB200_OK;
     }
 
-    const bool aligned = aligned_f32(d_in, in_stride, packed);
-    long long m_done = 0;
-    bool fused_done = false;
-
-    // ---- tensor-staged fast FIR (ddc_kernel_ws.cuh), R = 8 outputs per thread at every decimation ------------------------------
-    //   D = 32 / 64: sliced staging, where the direct form is FP32-bound (4 T / D flop per sample against 4 + 8 / D bytes at the
-    //   measured ridge of 11.4 flop/B); HBM-bound cells stay on the phase-major kernel, which over-fetches nothing.
-    //   D = 4 / 8, up to 1024 taps: whole blocks, two CTAs per SM (sixteen compute warps) -- measured at N = 2^26 against the tile
-    //   kernel: D = 4: T = 64 0.085 vs 0.128 ms, 128 0.126 vs 0.173, 256 0.234 vs 0.274, 512 0.456 vs 0.503, 1024 0.895 vs 0.981;
-    //   D = 8: T = 64 0.054 vs 0.062, 128 0.070 vs 0.083, 256 0.122 vs 0.141, 512 0.229 vs 0.265, 1024 0.449 vs 0.545.
-    //   D = 16: whole-row tiles for the HBM-bound filters only (T <= 128: 0.0517 against 0.0524 / 0.0537 ms of the 1-D bulk-copy
-    //   kernel); longer filters are much slower here than in ddc_kernel_w.cuh (T = 256: 0.312 vs 0.244 ms at 2^28).
-    // The kernel pads the filter to 8, 16, 32, 48, 64 or a multiple of 32 tap blocks, the tile kernel to a multiple of its R (16 / 8 at
-    // D = 4 / 8): auto only where the padded work is within 12 % of the tile kernel's (its deficit there: 84-94 % against 99 %).
-    if (aligned && pow2_d && fv != 1) {
-        const int r_tile = 64 / D;   // outputs per thread of the tile kernel
-        const bool fp32_bound = 4.0 * T / D > 11.4 * (4.0 + 8.0 / D);
-        const int jt_ws = Jp <= 8 ? 8 : (Jp <= 64 ? (Jp + 15) / 16 * 16 : (Jp + 31) / 32 * 32);   // the instantiations of k_ws.inc
-        const int j_tile = (Jp + r_tile - 1) / r_tile * r_tile;
-        const bool pad_ok = jt_ws * 100 <= j_tile * 112;
-        const bool auto_ws = (D == 4 && T <= 1024 && pad_ok) || (D == 8 && T <= 1024 && pad_ok) || (D == 16 && T <= 128) ||
-                             ((D == 32 || D == 64) && fp32_bound);
-        if (Jp <= (D == 4 ? 256 : (D == 8 ? 128 : 32)) && T >= D && (fv == 11 || (fv == 0 && auto_ws))) {
-            const long long n_blocks = (n_samples / (8LL * D)) * 8;         // whole thread-rows of 8 blocks: the tensor map covers exactly these
-            long long m_f = n_blocks * D >= T ? (n_blocks * D - T) / D + 1 : 0;   // outputs whose window lies inside them
-            if (m_f > M) m_f = M;
-            // chunk_of() divides by multiplication: exact while total chunks x chunks per stream < 2^64
-            if ((double)((m_f + 255) / 256) * (double)((m_f + 255) / 256) * (double)n_streams >= 1.8e19) m_f = 0;
-            if (m_f > 0) {
-                p.n_out = m_f;
-                p.tiles_per_stream = (m_f + 255) / 256;
-                p.total_tiles = p.tiles_per_stream * n_streams;
-                p.n_taps = jt_ws * D;
-                p.n_tap_blocks = jt_ws;
-                p.m_begin = 0;
-                int rc2 = ddch::launch_ws(h, p, reinterpret_cast<const float*>(d_in), n_blocks / 8, st, step, D, jt_ws);
-                if (rc2) return rc2;
-                p.n_out = M;
-                m_done = m_f;      // the few outputs that need the last partial thread-row come from the generic kernel below
-                fused_done = true;
-            }
-        }
-    }
-
-    // ---- ring kernels on 1-D bulk copies: fast FIR (D = 16, up to 64 tap blocks) / phase-major direct form (D = 32, 64, up to
-    // 16 tap blocks: the HBM-bound cells there; the FP32-bound ones went to the sliced kernel above) -----------------------------
-    if (!fused_done && aligned && ((D == 16 && Jp <= 64) || ((D == 32 || D == 64) && Jp <= 16)) && (fv == 0 || fv == 7 || fv == 8)) {
-        const int jt = Jp <= 4 ? 4 : (Jp <= 8 ? 8 : (Jp <= 16 ? 16 : (Jp <= 32 ? 32 : 64)));
-        ring_geometry(jt);
-        if (D == 16) return ddch::launch_w(h, p, st, step, D, jt);
-        std::vector<float2> ctp((size_t)jt * D);
-        make_ctaps(h, step, jt * D, ctp.data());
-        return ddch::launch_pd(h, p, ctp.data(), st, D, jt);
-    }
-
-    // ---- rotating-window tile kernel: any tap count up to 2048 at D = 4 .. 64 ---------------------------------------------------
-    int n_taps_pad = T;
-    if (!fused_done && aligned && pow2_d && fv != 1) {
-        const int R = 64 / D;
-        // tap split 2 (16 compute warps) whenever it costs no extra zero taps; option "variant" 2 / 3 force KS 1 / 2
-        int ks = (Jp % (2 * R) == 0 && R <= 4) ? 2 : 1;
-        if (fv == 2) ks = 1;
-        if (fv == 3 && R <= 4) ks = 2;
-        const int J = ((Jp + ks * R - 1) / (ks * R)) * (ks * R);  // each thread's tap-block loop is unrolled R times
-        if (J * D <= 2048) {
-            n_taps_pad = J * D;
-            std::vector<float2> ct((size_t)n_taps_pad);
-            make_ctaps(h, step, n_taps_pad, ct.data());
-            const long long tile_out = 256LL * R;
-            p.tiles_per_stream = (M + tile_out - 1) / tile_out;   // the last one may be ragged
+    if (plan.family == KF_WS) {
+        // tensor-staged / sliced fast FIR: its tensor map covers whole thread-rows of 8 blocks; the few outputs that need the last
+        // partial thread-row come from the generic kernel below.  Inputs shorter than one thread-row re-plan without it.
+        const long long n_blocks = (n_samples / (8LL * D)) * 8;
+        long long m_f = n_blocks * D >= T ? (n_blocks * D - T) / D + 1 : 0;   // outputs whose window lies inside them
+        if (m_f > M) m_f = M;
+        // chunk_of() divides by multiplication: exact while total chunks x chunks per stream < 2^64
+        if ((double)((m_f + 255) / 256) * (double)((m_f + 255) / 256) * (double)n_streams >= 1.8e19) m_f = 0;
+        if (m_f > 0) {
+            p.n_out = m_f;
+            p.tiles_per_stream = (m_f + 255) / 256;
             p.total_tiles = p.tiles_per_stream * n_streams;
-            p.n_taps = n_taps_pad;
-            p.n_tap_blocks = J;
-            p.halo_rows = (J + R - 2) / R;   // a thread-row reads blocks 0 .. J+R-2 of its own row space
+            p.n_taps = plan.jt * D;
+            p.n_tap_blocks = plan.jt;
             p.m_begin = 0;
-            int rc2 = ddch::launch_tile(h, p, ct.data(), st, D, ks);
+            int rc2 = ddch::launch_ws(h, p, reinterpret_cast<const float*>(d_in), n_blocks / 8, st, step, D, plan.jt);
             if (rc2) return rc2;
-            m_done = M;
+            p.n_out = M;
+            m_done = m_f;
             fused_done = true;
+        } else {
+            plan = plan_kernel(T, D, packed, aligned, fv, h->packed_engine, tensor_ok, 1u << KF_WS);
         }
+    }
+
+    if (plan.family == KF_W || plan.family == KF_PD) {
+        ring_geometry(plan.jt);
+        if (plan.family == KF_W) return ddch::launch_w(h, p, st, step, D, plan.jt);
+        std::vector<float2> ctp((size_t)plan.jt * D);
+        make_ctaps(h, step, plan.jt * D, ctp.data());
+        return ddch::launch_pd(h, p, ctp.data(), st, D, plan.jt);
+    }
+
+    if (plan.family == KF_TILE) {
+        const int R = 64 / D;
+        const int n_taps_pad = plan.jt * D;
+        std::vector<float2> ct((size_t)n_taps_pad);
+        make_ctaps(h, step, n_taps_pad, ct.data());
+        const long long tile_out = 256LL * R;
+        p.tiles_per_stream = (M + tile_out - 1) / tile_out;   // the last one may be ragged
+        p.total_tiles = p.tiles_per_stream * n_streams;
+        p.n_taps = n_taps_pad;
+        p.n_tap_blocks = plan.jt;
+        p.halo_rows = (plan.jt + R - 2) / R;   // a thread-row reads blocks 0 .. J+R-2 of its own row space
+        p.m_begin = 0;
+        int rc2 = ddch::launch_tile(h, p, ct.data(), st, D, plan.ks);
+        if (rc2) return rc2;
+        m_done = M;
+        fused_done = true;
     }
 
     if (m_done < M) {
@@ -658,6 +684,20 @@ int64_t ddcb200_out_len(int64_t n_samples, int n_taps, int decimation) {
     if (n_samples <= 0 || n_taps <= 0 || decimation <= 0) return 0;
     const int64_t full = (n_samples >= n_taps ? n_samples - n_taps : n_taps - n_samples) + 1;
     return (full + decimation - 1) / decimation;
+}
+
+int ddcb200_plan(int n_taps, int decimation, int packed, int aligned, int variant, int packed_engine, char* name, int name_cap) {
+    if (n_taps <= 0 || decimation <= 0 || !name || name_cap < 24) return fail(DDCB200_EINVAL, "plan: bad arguments");
+    const bool tensor_ok = packed && ddch::tc10_supported(nullptr, n_taps, decimation);
+    KernelPlan pl = plan_kernel(n_taps, decimation, packed != 0, aligned != 0, variant, packed_engine, tensor_ok);
+    if (pl.family == KF_UNPACK_F32) {
+        // the unpack stage writes 16-byte aligned float32 rows, whatever the packed rows were
+        pl = plan_kernel(n_taps, decimation, false, true, variant, packed_engine, false);
+        snprintf(name, (size_t)name_cap, "%s:%s", kFamilyName[KF_UNPACK_F32], kFamilyName[pl.family]);
+    } else {
+        snprintf(name, (size_t)name_cap, "%s", kFamilyName[pl.family]);
+    }
+    return pl.jt;
 }
 
 int ddcb200_set_taps(ddcb200_t* h, const double* taps, int n_taps) {

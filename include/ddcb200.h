@@ -61,6 +61,16 @@ int ddcb200_set_decimation(ddcb200_t* handle, int decimation);
  * (ddc.py:98,119).  Returns 0 for n_samples <= 0. */
 int64_t ddcb200_out_len(int64_t n_samples, int n_taps, int decimation);
 
+/* Which kernel family the dispatcher chooses for a call -- a pure function of the filter length, the decimation, the input
+ * type and alignment and the two selection options, so the selection table can be checked without a GPU (the reference has
+ * one code path, ddc.py:121-188; this is the drop-in's map of it onto kernels).
+ *   aligned        rows start on 16-byte boundaries (float32: pointer % 16 == 0 and stride % 4 == 0; packed: stride % 16 == 0)
+ *   variant, packed_engine   the options of ddcb200_set_option (0 / 1 are the defaults)
+ * Writes the family into `name` ("tensor10", "w10s", "ws", "w", "pd", "tile", "generic"; packed input without a fused-unpack
+ * kernel: "unpack+f32:" followed by the float32 family) and returns the tap-block count the kernel is instantiated for (0 where
+ * it has none), or a negative DDCB200_E* code. */
+int ddcb200_plan(int n_taps, int decimation, int packed, int aligned, int variant, int packed_engine, char* name, int name_cap);
+
 /* ---- device-resident entry points (inputs and outputs already in HBM) ------------------------------------
  * Replace _mix + _bandpass_fir_filter + _decimate (ddc.py:51-66, 85-100, 102-119) and the NCO generation of
  * cwg.generate_carrier_wave(complex=True) (cwg.py:31-36) for `n_streams` independent 1-D streams.

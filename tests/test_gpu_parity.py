@@ -628,3 +628,33 @@ def test_optional_kernel_variants_stay_correct(taps_dir, variant, name, dec):
         for s0 in (0, 35_000, m - 512):
             ref = orc.ddc_windowed_f64(xs[s], s0, 512, step, ddc.ddc_filter_coeffs, dec)
             assert np.abs(y[s, s0:s0 + 512] - ref).max() <= TOL_MAX * scale, (variant, s, s0)
+
+
+def test_last_variant_agrees_with_the_plan(tmp_path):
+    """ddcb200_plan (the selection table checked on the CPU in test_host_logic.py) names the family that actually runs."""
+    import ctypes
+
+    from scipy import signal
+
+    from dc_sand_b200 import _lib
+
+    prefix = {"tensor10": "tensor_fir_packed10<", "w10s": "fused_fast_fir_packed10_split<", "w": "fused_fast_fir<", "pd": "fused_phase_major_deferred<",
+              "tile": "fused_tma<", "generic": "generic<", "ws": ("fused_fast_fir_row_staged<", "fused_fast_fir_tensor_staged<", "fused_fast_fir_sliced<")}
+    n = 1 << 17
+    x = synth.digitiser_stream_fast(n, 9)
+    for d, t, packed, engine in [(16, 256, False, 1), (16, 64, False, 1), (4, 512, False, 1), (8, 300, False, 1), (32, 128, False, 1), (64, 1024, False, 1),
+                                 (3, 100, False, 1), (16, 256, True, 1), (16, 256, True, 0), (8, 128, True, 0), (12, 60, True, 1)]:
+        ddc = DigitalDownConverter(d, FS, _custom_taps(tmp_path, signal.firwin(t, min(0.8 / d, 0.99))))
+        ddc.set_option("packed_engine", engine)
+        buf = ctypes.create_string_buffer(64)
+        _lib.load().ddcb200_plan(t, d, int(packed), 1, 0, engine, buf, 64)
+        fam = buf.value.decode()
+        xin = torch.from_numpy(orc.pack10(x) if packed else x.astype(np.float32)).cuda()[None]
+        ddc.run_tensor(xin, 100e6, packed=packed)
+        got = ddc.last_variant
+        if fam.startswith("unpack+f32:"):
+            assert got.startswith("unpack10+"), (d, t, fam, got)
+            got, fam = got[len("unpack10+"):], fam[len("unpack+f32:"):]
+        assert got.startswith(prefix[fam]), (d, t, packed, engine, fam, ddc.last_variant)
+        ddc.close()
+

@@ -34,6 +34,49 @@ def test_out_len_matches_reference_lengths(meta):
     assert lib.ddcb200_out_len(1 << 28, 256, 16) == 16777201
 
 
+def _plan(t, d, packed=0, aligned=1, variant=0, packed_engine=1):
+    buf = ctypes.create_string_buffer(64)
+    jt = _lib.load().ddcb200_plan(t, d, packed, aligned, variant, packed_engine, buf, 64)
+    return buf.value.decode(), jt
+
+
+def test_kernel_selection_table():
+    """The dispatcher's selection is a pure function (ddcb200_plan): the BASELINE configs[3] grid (taps 64-1024 x decimation
+    4-64) maps onto the kernel families DESIGN.md section 4 names, for float32 and for packed input on both engines, and the
+    corners fall through to the tile / generic kernels."""
+    taps_axis = (64, 128, 256, 512, 1024)
+    f32 = {
+        4: [("ws", 16), ("ws", 32), ("ws", 64), ("ws", 128), ("ws", 256)],
+        8: [("ws", 8), ("ws", 16), ("ws", 32), ("ws", 64), ("ws", 128)],
+        16: [("ws", 8), ("ws", 8), ("w", 16), ("w", 32), ("w", 64)],           # HBM-bound filters on whole-row tiles, then the fast FIR
+        32: [("pd", 4), ("pd", 4), ("pd", 8), ("ws", 16), ("ws", 32)],         # phase-major while HBM-bound, sliced when FP32-bound
+        64: [("pd", 4), ("pd", 4), ("pd", 4), ("pd", 8), ("ws", 16)],
+    }
+    for d, row in f32.items():
+        assert [_plan(t, d) for t in taps_axis] == row, d
+        # packed input: the tensor engine in every cell; on the CUDA cores the unpack stage + the float32 family of the cell,
+        # except the one cell with a fused-unpack CUDA-core kernel (D = 16, 129 .. 256 taps)
+        assert [_plan(t, d, packed=1)[0] for t in taps_axis] == ["tensor10"] * 5, d
+        want = [("unpack+f32:" + f, jt) for f, jt in row]
+        if d == 16:
+            want[2] = ("w10s", 16)
+        assert [_plan(t, d, packed=1, packed_engine=0) for t in taps_axis] == want, d
+    assert _plan(256, 16) == ("w", 16)                            # the headline configuration
+    assert _plan(200, 16) == ("w", 16) and _plan(2, 16) == ("w", 4)
+    assert _plan(300, 8) == ("tile", 40)                          # padding to 48 blocks would cost more than 12 %
+    assert _plan(2048, 4) == ("tile", 512)
+    assert _plan(256, 3) == ("generic", 0)                        # odd decimation
+    assert _plan(4096, 16) == ("generic", 0)                      # more taps than any fused kernel holds
+    assert _plan(256, 16, aligned=0) == ("generic", 0)            # rows not 16-byte aligned
+    assert _plan(256, 16, variant=1) == ("generic", 0)
+    assert _plan(256, 16, packed=1, aligned=0) == ("unpack+f32:w", 16)
+    assert _plan(256, 12, packed=1) == ("unpack+f32:generic", 0)
+    assert _plan(256, 16, packed=1, variant=13, packed_engine=0) == ("tensor10", 0)   # forced
+    assert _plan(256, 32, variant=8) == ("pd", 8) and _plan(256, 16, variant=8) == ("w", 16)   # a variant that is not built falls through
+    buf = ctypes.create_string_buffer(8)
+    assert _lib.load().ddcb200_plan(256, 16, 0, 1, 0, 1, buf, 8) == _lib.EINVAL
+
+
 def test_library_fails_loudly_without_gpu():
     import torch
 
