@@ -31,8 +31,6 @@ struct RunParams {
     int n_streams;
     int vec_store;               // 1 if out pointer / stride allow 16-byte stores
     unsigned long long* dbg;     // optional diagnostic counters (wait cycles / total cycles of compute warps), or NULL
-    int l2_ahead;                // kernel P: chunks of L2 prefetch distance (0 = off)
-    int stagger_cycles;          // start delay of every other compute warp (see ddc_fused_kernel)
     int debug_mode;              // 0 normal; 1 compute only (no TMA, no waits); 2 memory only (no FIR) -- ceilings for tuning
     unsigned long long cps_magic;// kernel WS: ceil(2^64 / tiles_per_stream), 0 when tiles_per_stream == 1 (see chunk_of)
 };

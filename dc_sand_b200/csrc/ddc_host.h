@@ -48,8 +48,6 @@ struct ddcb200 {
     int64_t launches = 0;
     int force_variant = 0;
     int debug_mode = 0;
-    int stagger_cycles = 0;
-    int l2_ahead = 0;
     unsigned long long* d_dbg = nullptr;   // diagnostic counters (option "dbg_counters")
     std::string last_variant = "none";
     bool smem_attr_set = false;

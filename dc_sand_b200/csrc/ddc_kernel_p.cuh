@@ -67,7 +67,7 @@ struct PCfg {
 };
 
 // =============================================================================================================
-// Default float32 variant: same ring and FIR as ddc_fused_p_kernel<KS = 1>, but the epilogue of chunk i (NCO rotation,
+// The kernel: ring and FIR as described above, and the epilogue of chunk i (NCO rotation,
 // address arithmetic, stores: ~160 mostly dependent instructions) is DEFERRED into the first phase-group pass of chunk
 // i + 1, where it sits in the same basic block as 512 independent FFMA2 and the scheduler hides its latency chains
 // between them.  Stand-alone, every epilogue left the FMA pipe to the other warp of the sub-partition for ~500 cycles.
@@ -105,7 +105,7 @@ ddc_fused_pd_kernel(const __grid_constant__ RunParams p, const __grid_constant__
     const unsigned long long chunk_dph = (unsigned long long)((long long)C::CHUNK_OUT * D) * p.step_fx;
 
     if (warp >= NWARPS) {
-        // ------------------------------------------------------------------ producer warps (see ddc_fused_p_kernel)
+        // ------------------------------------------------------------------ producer warps
         constexpr int NP = C::NPROD;
         const int pid = warp - NWARPS;
         const long long pstride = (long long)NP * gridDim.x;
@@ -115,12 +115,6 @@ ddc_fused_pd_kernel(const __grid_constant__ RunParams p, const __grid_constant__
         const int sbase = C::sub_base(pid), scnt = C::sub_count(pid);
         int sidx = 0;
         uint32_t par = 1;
-        // L2 prefetch cursor: this producer's chunk `l2_ahead` iterations from now.  The ring can only keep ~5 chunks
-        // (87 KB) in flight per SM, less than bandwidth x HBM latency under load; pulling future chunks into the 126 MB
-        // L2 first means the ring only has to cover the L2 -> shared-memory latency.
-        const int pf_ahead = p.l2_ahead;
-        const long long pf_first = pfirst + (long long)pf_ahead * pstride;
-        int pcs = (int)(pf_first / cps), pcc = (int)(pf_first % cps);
         for (int k = pid; k < n_k && (p.debug_mode & 255) != 1; k += NP) {
             const int slot = sbase + sidx;
             const bool leader = elect_one();
@@ -167,17 +161,6 @@ ddc_fused_pd_kernel(const __grid_constant__ RunParams p, const __grid_constant__
                 }
             }
             __syncwarp();
-            if (pf_ahead > 0) {
-                if (leader && k + pf_ahead * NP < n_k) {
-                    const long long pvalid = p.n_samples - (long long)pcc * C::CHUNK_S;
-                    const uint32_t nb = (uint32_t)((pvalid < C::CHUNK_S ? pvalid : C::CHUNK_S) * 4) & ~15u;
-                    const float* pf = reinterpret_cast<const float*>(p.in) + (long long)pcs * p.in_stride + (long long)pcc * C::CHUNK_S;
-                    if (nb) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf), "r"(nb) : "memory");
-                }
-                pcs += gs;
-                pcc += gc;
-                if (pcc >= cps) { pcc -= cps; ++pcs; }
-            }
             if (++sidx == scnt) { sidx = 0; par ^= 1u; }
             cs += gs;
             cc += gc;
@@ -232,11 +215,6 @@ ddc_fused_pd_kernel(const __grid_constant__ RunParams p, const __grid_constant__
             }
         };
 
-        if (p.stagger_cycles > 0 && grp > 0) {   // spread the chunk boundaries of the eight groups over one chunk time
-            const long long t0 = clock64();
-            const long long wait = (long long)grp * p.stagger_cycles;
-            while (clock64() - t0 < wait) {}
-        }
         long long t_wait = 0;
         const long long t_begin = clock64();
         for (int k = grp; k < n_k; k += NG) {
@@ -276,7 +254,7 @@ ddc_fused_pd_kernel(const __grid_constant__ RunParams p, const __grid_constant__
                 xoff = 4;
                 tp += 2;
             }
-            // ---- remaining phase groups (see ddc_fused_p_kernel for the two induction variables)
+            // ---- remaining phase groups
 #pragma unroll 1
             for (int pg = 1; pg < C::V; ++pg, tp += 2) {
                 asm volatile("" : "+r"(xoff));

@@ -157,14 +157,6 @@ ddc_fused_kernel(const __grid_constant__ RunParams p, const __grid_constant__ Ta
             rot_thr[r] = nco_rot((unsigned long long)((long long)(g * R + rbeg + r) * D) * p.step_fx);
         const unsigned long long tile_dph = (unsigned long long)((long long)TILE_OUT * D) * p.step_fx;
 
-        // The two (KS = 1) or four (KS = 2) compute warps that share an SM sub-partition do identical work and would reach
-        // their epilogues together, leaving the FMA pipe idle; starting every other one half a tile late keeps one
-        // warp in its FMA loop while its neighbour rotates and stores.
-        if (p.stagger_cycles > 0 && ((warp >> 2) & 1)) {
-            const long long t0 = clock64();
-            while (clock64() - t0 < p.stagger_cycles) {}
-        }
-
         for (int it = 0; it < n_iter; ++it) {
             const int stage = it % STAGES;
             const uint32_t ph = (uint32_t)(it / STAGES) & 1u;

@@ -8,8 +8,8 @@
 namespace ddck {
 
 // ---------------------------------------------------------------------------------------------------------------------
-// packed 10-bit input (BASELINE configs[2]; reference stub ddc.py:68-83): raw TMA ring + in-warp unpack as in
-// ddc_fused_p10_kernel, with the fast FIR and the deferred branch-free epilogue.  The unpack avoids I2F (quarter-rate
+// packed 10-bit input (BASELINE configs[2]; reference stub ddc.py:68-83): raw TMA ring, unpack warps, the fast FIR and the
+// deferred branch-free epilogue of ddc_kernel_w.cuh.  The unpack avoids I2F (quarter-rate
 // conversion pipe): the 10 bits are placed in the mantissa of 2^23 with the sign bit flipped,
 //      as_float(((word >> s) & 0x3FF) ^ 0x4B000200) = 2^23 + (v + 512),      v = that value - (2^23 + 512)   (exact),
 // i.e. one shift, one LOP3 and one FADD per sample -- bit-exact for all 1024 codes (tests/test_gpu_parity.py).

@@ -327,8 +327,6 @@ int run_device(ddcb200* h, const void* d_in, bool packed, int64_t n_samples, int
     p.phase0_fx = phase_of(step, sample_offset);
     p.vec_store = ((reinterpret_cast<uintptr_t>(d_out) % 16) == 0 && (out_stride % 2) == 0) ? 1 : 0;
     p.debug_mode = h->debug_mode;
-    p.stagger_cycles = h->stagger_cycles;
-    p.l2_ahead = h->l2_ahead;
     p.dbg = h->d_dbg;
 
     // ring kernels (ddc_kernel_p / _w / _w10.cuh): chunks of 32 thread-rows of 128 samples
@@ -1051,14 +1049,6 @@ int ddcb200_set_option(ddcb200_t* h, const char* key, int64_t value) {
     if (!strcmp(key, "tc_na") || !strcmp(key, "tc_nraw")) {   // tuning: pipeline depths of the tensor engine (0 = automatic)
         if (value < 0 || value > 8) return fail(DDCB200_EINVAL, "%s must be 0 .. 8", key);
         (key[4] == 'a' ? h->tc_na : h->tc_nraw) = (int)value;
-        return DDCB200_OK;
-    }
-    if (!strcmp(key, "l2_ahead")) {
-        h->l2_ahead = (int)value;
-        return DDCB200_OK;
-    }
-    if (!strcmp(key, "stagger_cycles")) {
-        h->stagger_cycles = (int)value;
         return DDCB200_OK;
     }
     if (!strcmp(key, "debug_mode")) {

@@ -203,7 +203,7 @@ const char* ddcb200_last_variant(ddcb200_t* handle);
  *                    (decimation 4 .. 64 a power of two, 16-byte aligned rows, filter fits shared memory), 0 the CUDA-core
  *                    kernels; float32 input always runs on the CUDA cores;
  *   "tc_ns", "tc_na", "tc_nraw"   tuning of the tensor engine (row width, A stages, raw slots; 0 = automatic);
- *   "debug_mode", "dbg_counters", "l2_ahead", "stagger_cycles"   measurement aids of the kernels (compute-only / memory-only
+ *   "debug_mode", "dbg_counters"   measurement aids of the kernels (compute-only / memory-only
  *                    ceilings, ring wait-time counters). */
 int ddcb200_set_option(ddcb200_t* handle, const char* key, int64_t value);
 
