@@ -430,16 +430,50 @@ def run_ours(args):
     parity_err = parity_window(ddc, d_in, d_out, packed, n, T, D, seed=rank)
 
     # ---- e2e: pinned host buffers through the C ABI (H2D + kernel + D2H per step) ---------------------------------
-    h_in = torch.empty(d_in.shape, dtype=d_in.dtype, pin_memory=True)
-    h_in.copy_(d_in)
-    h_out = torch.empty((n_streams, m), dtype=torch.complex64, pin_memory=True)
+    # Several ranks of one box share its host links, and not evenly (profiles/r2_n8_placement.txt), while what bounds a
+    # host-fed step is exactly that link: the end-to-end leg of the multi-GPU job therefore shards the SAME 128 streams by the
+    # host-to-device rate each rank measures with all ranks copying at once (scheduler.weighted_shard_sizes; equal shards when
+    # the rates agree within 15 %).  The device-resident leg above keeps the balanced shards: there the GPU is the bound.
+    e2e_streams, e2e_sizes, probe_rates = n_streams, None, None
+    if world > 1 and not packed and not args.streams:
+        from dc_sand_b200.scheduler import weighted_shard_sizes
+
+        forced = os.environ.get("DDCB200_E2E_WEIGHTS")          # "w0,w1,..." (testing); "equal" switches the weighting off
+        if forced == "equal":
+            probe_rates = [1.0] * world
+        elif forced:
+            probe_rates = [float(v) for v in forced.split(",")]
+        else:
+            pb = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
+            db = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+            db.copy_(pb, non_blocking=True)
+            torch.cuda.synchronize()
+            barrier()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            for _ in range(3):
+                db.copy_(pb, non_blocking=True)
+            p1.record()
+            torch.cuda.synchronize()
+            mine = torch.tensor([3 * (256 << 20) / (p0.elapsed_time(p1) * 1e-3) / 1e9], dtype=torch.float64, device=dev)
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            probe_rates = [float(v.item()) for v in allr]
+            del pb, db
+        e2e_sizes = weighted_shard_sizes(TOTAL_STREAMS_C5, probe_rates)
+        e2e_streams = e2e_sizes[rank]
+    h_in = torch.empty((e2e_streams, d_in.shape[1]), dtype=d_in.dtype, pin_memory=True)
+    for r0 in range(0, e2e_streams, n_streams):                  # a rank with more streams than its device-resident shard repeats rows
+        cnt = min(n_streams, e2e_streams - r0)
+        h_in[r0:r0 + cnt].copy_(d_in[:cnt])
+    h_out = torch.empty((e2e_streams, m), dtype=torch.complex64, pin_memory=True)
     torch.cuda.synchronize()
     step = ddc.phase_step(n, FC)
     fn = lib.ddcb200_run_host_packed10 if packed else lib.ddcb200_run_host_f32
     h = ddc._get_handle()
 
     def e2e_pass():
-        _lib.check(fn(h, h_in.data_ptr(), n, n_streams, h_in.stride(0), step, 0, h_out.data_ptr(), m), "run_host")
+        _lib.check(fn(h, h_in.data_ptr(), n, e2e_streams, h_in.stride(0), step, 0, h_out.data_ptr(), m), "run_host")
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     e2e_pass()
@@ -450,8 +484,11 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     # (tolerance, not bit equality: the host path runs time chunks, which may pair outputs differently in the fast FIR)
-    a_dev, a_host = d_out[:, : min(m, 4096)].cpu(), h_out[:, : min(m, 4096)]
+    rows = min(e2e_streams, n_streams)
+    a_dev, a_host = d_out[:rows, : min(m, 4096)].cpu(), h_out[:rows, : min(m, 4096)]
     same = bool((a_dev - a_host).abs().max() <= 1e-5 * a_dev.abs().max())
+    e2e_in_bytes = h_in.numel() * h_in.element_size()
+    e2e_out_bytes = e2e_streams * m * 8
     del h_in, h_out
 
     # ---- optional final gather of the outputs over NCCL (outside the timed region; the hot path has no collective) ---
@@ -522,12 +559,17 @@ def run_ours(args):
             "e2e": {
                 "value": total_streams * n / e2e_s / 1e9,
                 "unit": "Gsamples/s",
-                "h2d_bytes_per_step": in_bytes,
-                "d2h_bytes_per_step": out_bytes,
+                "h2d_bytes_per_step": e2e_in_bytes,
+                "d2h_bytes_per_step": e2e_out_bytes,
                 "ms_per_step": e2e_s * 1e3,
                 "steps": e2e_steps,
                 "api": "ddcb200_run_host_* (C ABI, pinned host buffers, complex64 out)",
                 "matches_device_path": same,
+                # multi-GPU: streams per rank of this leg and the probe behind them (bytes above are rank 0's)
+                "streams_per_rank": e2e_sizes,
+                "host_link_probe_gbps": None if probe_rates is None else [round(v, 1) for v in probe_rates],
+                "partition": None if e2e_sizes is None else "streams sharded in proportion to each rank's host-to-device rate with all ranks "
+                                                            "copying at once (dc_sand_b200.scheduler.weighted_shard_sizes; balanced within 15 %)",
             },
             "parity_max_err": parity_err,
             "parity_check": "max over ranks of |y - float64 windowed oracle| / max|y| on two 512-output windows per rank (tolerance 1e-5)",

@@ -58,6 +58,46 @@ def shard_sizes(n_streams: int, world_size: int) -> list[int]:
     return [b - a for a, b in (shard_range(n_streams, world_size, r) for r in range(world_size))]
 
 
+def weighted_shard_sizes(n_streams: int, weights: Sequence[float], tolerance: float = 0.15) -> list[int]:
+    """Streams per rank in proportion to `weights` (largest-remainder apportionment, every rank keeps at least one stream
+    while there are enough).
+
+    For the END-TO-END path of a box whose GPUs do not share the host evenly: streams are independent, so the partition is
+    free, and what bounds a host-fed job is each rank's share of the host links, not its GPU (devices 0 .. 3 of this pool's
+    8 x B200 boxes get ~25 GB/s each when all eight copy at once, devices 4 .. 7 ~47 GB/s: profiles/r2_n8_placement.txt).
+    `weights` are the per-rank host-to-device rates measured with all ranks copying at once (bench.py does that in front of
+    its end-to-end leg).  Weights within `tolerance` of each other (max / min - 1) give the balanced shard_sizes(): a noisy
+    probe must not unbalance a symmetric box."""
+    w = [float(v) for v in weights]
+    world = len(w)
+    if world == 0 or any(not (v > 0.0) or v != v or v == float("inf") for v in w):
+        raise ValueError(f"weights must be positive and finite: {weights!r}")
+    if n_streams < 0:
+        raise ValueError("n_streams must be >= 0")
+    if max(w) / min(w) - 1.0 <= tolerance or n_streams < world:
+        return shard_sizes(n_streams, world)
+    total = sum(w)
+    quota = [n_streams * v / total for v in w]
+    sizes = [max(1, int(q)) for q in quota]
+    # hand out (or take back) the difference by largest (smallest) remainder; never below one stream
+    while sum(sizes) < n_streams:
+        r = max(range(world), key=lambda i: quota[i] - sizes[i])
+        sizes[r] += 1
+    while sum(sizes) > n_streams:
+        r = min((i for i in range(world) if sizes[i] > 1), key=lambda i: quota[i] - sizes[i])
+        sizes[r] -= 1
+    return sizes
+
+
+def weighted_shard_range(n_streams: int, weights: Sequence[float], rank: int, tolerance: float = 0.15) -> tuple[int, int]:
+    """Contiguous block of streams of `rank` under weighted_shard_sizes()."""
+    sizes = weighted_shard_sizes(n_streams, weights, tolerance)
+    if not (0 <= rank < len(sizes)):
+        raise ValueError(f"bad rank {rank} of {len(sizes)}")
+    start = sum(sizes[:rank])
+    return start, start + sizes[rank]
+
+
 class ShardedDDC:
     """One rank of a stream-sharded down-converter (one process per GPU, torch.distributed initialised by the caller).
 

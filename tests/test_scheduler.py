@@ -102,3 +102,32 @@ def test_device_placement_deals_ranks_over_both_halves():
             dev(0, 4, 8, bad)
     with pytest.raises(ValueError):
         dev(4, 4, 8)
+
+
+def test_weighted_shard_sizes():
+    """Host-link-aware partition of the end-to-end leg: proportional to the measured rates, every stream assigned once, at
+    least one stream per rank, and a symmetric box (rates within the tolerance) keeps the balanced shards."""
+    from dc_sand_b200.scheduler import shard_sizes, weighted_shard_range, weighted_shard_sizes
+
+    assert weighted_shard_sizes(128, [25, 25, 25, 25, 47, 47, 47, 47]) == [11, 11, 11, 11, 21, 21, 21, 21]
+    assert weighted_shard_sizes(128, [50, 51, 49, 50]) == shard_sizes(128, 4)          # within 15 %: balanced
+    assert weighted_shard_sizes(128, [1, 3]) == [32, 96]
+    assert weighted_shard_sizes(10, [1, 1000]) == [1, 9]                                # nobody is left without a stream
+    assert weighted_shard_sizes(3, [1, 100, 1, 1]) == shard_sizes(3, 4)                 # fewer streams than ranks
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        world = int(rng.integers(1, 9))
+        n = int(rng.integers(world, 300))
+        w = rng.uniform(5.0, 60.0, size=world)
+        sizes = weighted_shard_sizes(n, w)
+        assert sum(sizes) == n and min(sizes) >= 1
+        spans = [weighted_shard_range(n, w, r) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        if max(w) / min(w) > 1.15:
+            t = [s / v for s, v in zip(sizes, w)]        # time per rank ~ streams / rate: within one stream of the ideal
+            ideal = n / w.sum()
+            assert max(t) <= ideal + 1.0 / min(w) + 1e-9
+    for bad in ([], [1.0, 0.0], [1.0, float("nan")], [1.0, -2.0]):
+        with pytest.raises(ValueError):
+            weighted_shard_sizes(8, bad)
+
