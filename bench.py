@@ -460,6 +460,8 @@ def run_ours(args):
             dist.all_gather(allr, mine)
             probe_rates = [float(v.item()) for v in allr]
             del pb, db
+        med = float(np.median(probe_rates))
+        probe_rates = [min(max(v, 0.5 * med), 2.0 * med) for v in probe_rates]   # one wild reading must not empty or flood a rank
         e2e_sizes = weighted_shard_sizes(TOTAL_STREAMS_C5, probe_rates)
         e2e_streams = e2e_sizes[rank]
     h_in = torch.empty((e2e_streams, d_in.shape[1]), dtype=d_in.dtype, pin_memory=True)
