@@ -77,6 +77,24 @@ def test_kernel_selection_table():
     assert _lib.load().ddcb200_plan(256, 16, 0, 1, 0, 1, buf, 8) == _lib.EINVAL
 
 
+def test_host_thread_pool(tmp_path):
+    """The pool of parked host threads that stages pageable input and widens complex128 output (csrc/host_pool.h): a C++
+    stress test, under ThreadSanitizer when g++ links it."""
+    import shutil
+    import subprocess
+
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    src = os.path.join(ROOT, "tests", "native", "host_pool_test.cpp")
+    inc = os.path.join(ROOT, "dc_sand_b200", "csrc")
+    exe = os.path.join(str(tmp_path), "host_pool_test")
+    base = ["g++", "-std=c++17", "-O1", "-g", "-pthread", "-Wall", "-Werror", "-I", inc, src, "-o", exe]
+    if subprocess.run(base + ["-fsanitize=thread"], capture_output=True).returncode != 0:
+        subprocess.run(base, check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "host pool OK" in out.stdout, out.stdout + out.stderr
+
+
 def test_library_fails_loudly_without_gpu():
     import torch
 
