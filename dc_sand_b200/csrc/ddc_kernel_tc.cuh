@@ -44,6 +44,16 @@
 #define DDCB200_TC_UB 3
 #endif
 
+// Per-tile event trace of CTA 0 (build with -DDDCB200_TC_TRACE, option dbg_counters = 3 prints it): clock64 of ten events
+// of the first 96 tiles, at p.dbg[64 + 96 * event + tile] -- how the hand-shakes of the five warp roles line up in time
+// (profiles/r2_tensor_engine_trace.md).
+#ifdef DDCB200_TC_TRACE
+#define TC_TRACE(ev, k) \
+    do { if (p.dbg && blockIdx.x == 0 && (k) < 96 && lane == 0) p.dbg[64 + 96 * (ev) + (k)] = (unsigned long long)clock64(); } while (0)
+#else
+#define TC_TRACE(ev, k) do { } while (0)
+#endif
+
 namespace ddck {
 
 struct TcParams {
@@ -249,6 +259,7 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
             const long long t0 = p.dbg ? clock64() : 0;
             mbar_wait_uni(&raw_empty[slot], par);
             if (p.dbg) tw0 += clock64() - t0;
+            TC_TRACE(0, k);
             const unsigned char* src = reinterpret_cast<const unsigned char*>(p.in) + (long long)cs * p.in_stride + (long long)cc * S::TILE_PACKED;
             unsigned char* dst = rsm + (size_t)slot * tc.raw_slot_bytes;
             const long long valid_s = p.n_samples - (long long)cc * S::TILE_S;   // samples of this stream from the tile start
@@ -294,6 +305,7 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
             const long long t1 = p.dbg ? clock64() : 0;
             mbar_wait_uni(&acc_empty[acc], cpar);
             if (p.dbg) { tw0 += t1 - t0; tw1 += clock64() - t1; }
+            TC_TRACE(4, k);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N);
             uint32_t a_lo = a_lo0 + (uint32_t)as * stage16;   // + one 16-byte row per H MMAs
@@ -309,6 +321,7 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
             }
             tc_commit_if(&a_empty[as], leader);      // the A stage may be overwritten once these MMAs have read it
             tc_commit_if(&acc_full[acc], leader);    // and the accumulator is complete
+            TC_TRACE(5, k);
             __syncwarp();
             if (++as == tc.n_a) { as = 0; apar ^= 1u; }
             acc ^= 1;
@@ -338,6 +351,7 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
             const long long t0 = p.dbg ? clock64() : 0;
             mbar_wait_uni(&acc_full[acc], fpar);
             if (p.dbg) tw0 += clock64() - t0;
+            if (warp == 4) TC_TRACE(6, k);
             tc_fence_after();
             const float2 rot0 = nco_rot_bf(row_ph + (unsigned long long)cc * tile_dph);
             float2* o = p.out + (long long)cs * p.out_stride + (long long)cc * TILE_OUT;
@@ -355,6 +369,7 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&acc_empty[acc]);   // accumulator back to the MMA warp
+                        if (warp == 4) TC_TRACE(7, k);
                     }
                     if ((p.debug_mode & 255) == 3) continue;   // debug_mode 3: no epilogue arithmetic or stores (tuning ceiling)
 #pragma unroll
@@ -388,6 +403,7 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
                     }
                 }
             }
+            if (warp == 4) TC_TRACE(8, k);
             acc ^= 1;
             if (acc == 0) fpar ^= 1u;
             cs += gs;
@@ -507,6 +523,7 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
             mbar_wait_uni(&a_empty[as], epar);
             const long long t2 = p.dbg ? clock64() : 0;
             if (p.dbg) tw0 += t2 - t0;
+            if (u == 0) TC_TRACE(1, k);
             unsigned char* sp = asm_ + (size_t)as * tc.a_stage_bytes + st_off;
 #pragma unroll
             for (int b = 0; b < UB; ++b) {
@@ -531,6 +548,9 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
             fence_proxy_async();   // my stores before the tensor core's reads of this stage
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[as]);
+            if (u == 0) TC_TRACE(2, k);
+            if (u == NU - 1) TC_TRACE(3, k);
+            if (u == 0 && early) TC_TRACE(9, k);
             if (more && !early) {
                 const long long t3 = p.dbg ? clock64() : 0;
                 mbar_wait_uni(&raw_full[rs], rpar);

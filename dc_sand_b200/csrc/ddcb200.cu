@@ -1002,17 +1002,19 @@ void* ddcb200_stream(ddcb200_t* h) { return h ? (void*)h->stream : nullptr; }
 int64_t ddcb200_launch_count(ddcb200_t* h) { return h ? h->launches : 0; }
 const char* ddcb200_last_variant(ddcb200_t* h) { return h ? h->last_variant.c_str() : "none"; }
 
+static constexpr size_t kDbgBytes = (64 + 10 * 96) * sizeof(unsigned long long);   // counters + the tensor engine's event trace
+
 int ddcb200_set_option(ddcb200_t* h, const char* key, int64_t value) {
     if (!h || !key) return fail(DDCB200_EINVAL, "set_option: bad arguments");
     if (!strcmp(key, "variant")) {
         h->force_variant = (int)value;
         return DDCB200_OK;
     }
-    if (!strcmp(key, "dbg_counters")) {   // 1: allocate + zero, 0: free, 2: print wait/total cycle ratio to stderr
+    if (!strcmp(key, "dbg_counters")) {   // 1: allocate + zero, 0: free, 2: print wait/total cycle ratio to stderr, 3: print the event trace
         DeviceGuard g(h->device);
         if (value == 1) {
-            if (!h->d_dbg) CUDA_TRY(cudaMalloc(&h->d_dbg, 128));
-            CUDA_TRY(cudaMemset(h->d_dbg, 0, 128));
+            if (!h->d_dbg) CUDA_TRY(cudaMalloc(&h->d_dbg, kDbgBytes));
+            CUDA_TRY(cudaMemset(h->d_dbg, 0, kDbgBytes));
         } else if (value == 2 && h->d_dbg) {
             unsigned long long v[2] = {0, 0};
             CUDA_TRY(cudaDeviceSynchronize());
@@ -1025,6 +1027,19 @@ int ddcb200_set_option(ddcb200_t* h, const char* key, int64_t value) {
                 if (w[3 * r + 2])
                     fprintf(stderr, "dbg_counters: tensor engine %-28s waits %.1f %% + %.1f %% of %llu cycles\n", role[r],
                             100.0 * w[3 * r] / w[3 * r + 2], 100.0 * w[3 * r + 1] / w[3 * r + 2], w[3 * r + 2]);
+        } else if (value == 3 && h->d_dbg) {   // event trace of the tensor engine (builds with -DDDCB200_TC_TRACE fill it)
+            std::vector<unsigned long long> tr(10 * 96);
+            CUDA_TRY(cudaDeviceSynchronize());
+            CUDA_TRY(cudaMemcpy(tr.data(), h->d_dbg + 64, tr.size() * 8, cudaMemcpyDeviceToHost));
+            unsigned long long t0 = ~0ull;
+            for (auto v : tr) if (v && v < t0) t0 = v;
+            fprintf(stderr, "tc_trace: tile  tma_issue unp_start unp0_done unpL_done raw_next mma_start mma_issued acc_full acc_freed epi_done  (clocks since the first event)\n");
+            static const int order[10] = {0, 1, 2, 3, 9, 4, 5, 6, 7, 8};
+            for (int k = 0; k < 96; ++k) {
+                fprintf(stderr, "tc_trace: %4d", k);
+                for (int e : order) fprintf(stderr, " %9lld", tr[96 * e + k] ? (long long)(tr[96 * e + k] - t0) : -1LL);
+                fprintf(stderr, "\n");
+            }
         } else if (value == 0 && h->d_dbg) {
             cudaFree(h->d_dbg);
             h->d_dbg = nullptr;
