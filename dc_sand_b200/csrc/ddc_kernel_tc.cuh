@@ -25,8 +25,9 @@
 //
 // Pipeline per CTA (one per SM, persistent, 8 + NUNP warps):
 //      warp 0      TMA producer: one bulk copy of packed bytes per tile -> raw ring (up to 8 slots: HBM latency)
-//      warps 8..   unpack: 20 bytes -> 16 fp16 per lane and group, bit-exact (PRMT, LOP3, IMAD.WIDE, LEA.HI, HFMA2 per sample
-//                  pair), raw words of the NEXT tile already in registers, two STS.128 per group into the sub-streams
+//      warps 8..   unpack, in two teams that take alternate tiles: 20 bytes -> 16 fp16 per lane and group, bit-exact (PRMT,
+//                  LOP3, IMAD.WIDE, LEA.HI, HFMA2 per sample pair), raw words of the team's NEXT tile already in registers,
+//                  two STS.128 per group into the sub-streams
 //      warp 1      one elected thread issues K / 16 tcgen05.mma per tile into one of two TMEM accumulators
 //      warps 4-7   epilogue: tcgen05.ld in the 16x256b fragment layout (a quad of lanes holds one row's outputs, so the warp's
 //                  stores cover whole sectors), hi + lo recombination and NCO rotation in four FFMA2 per output, streaming stores
@@ -42,6 +43,9 @@
 #endif
 #ifndef DDCB200_TC_UB
 #define DDCB200_TC_UB 3
+#endif
+#ifndef DDCB200_TC_TEAMS
+#define DDCB200_TC_TEAMS 2   // teams of unpack warps that take alternate tiles: six warps per tile, two tile times each (1: all twelve on every tile)
 #endif
 
 // Per-tile event trace of CTA 0 (build with -DDDCB200_TC_TRACE, option dbg_counters = 3 prints it): clock64 of ten events
@@ -217,8 +221,8 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
 #pragma unroll 1
         for (int s = 0; s < 8; ++s) {
             mbar_init(&raw_full[s], 1);
-            mbar_init(&raw_empty[s], NU);
-            mbar_init(&a_full[s], NU);
+            mbar_init(&raw_empty[s], NU / DDCB200_TC_TEAMS);
+            mbar_init(&a_full[s], NU / DDCB200_TC_TEAMS);
             mbar_init(&a_empty[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
@@ -478,26 +482,30 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
             if (cc >= cps) { cc -= cps; ++cs; }
         }
     } else if (warp >= 8) {
-        // ------------------------------------------------------------------ unpack warps: all of them share every tile
-        const int u = warp - 8;
+        // ------------------------------------------------------------------ unpack warps: NTEAM teams, team t takes the tiles
+        // k = t (mod NTEAM).  With all twelve warps on every tile the stage is handed over when the slowest of them has drained its
+        // stores behind the tensor core's operand reads, and the tensor pipe idled a third of every tile waiting for that
+        // (profiles/r2_tensor_engine_trace.md); a team of six has two tile times per tile (0.419 -> 0.405 ms on configs[2])
+        constexpr int NTEAM = DDCB200_TC_TEAMS, NUT = NU / NTEAM;   // teams, warps per team
+        static_assert(NU % NTEAM == 0, "teams of equal size");
+        const int team = (warp - 8) % NTEAM, u = (warp - 8) / NTEAM;   // my team takes the tiles k = team (mod NTEAM)
         // lane -> 16-sample group inside a run of 32 groups.  A quarter warp's two STS.128 must hit eight distinct 16-byte bank
         // groups: four even sub-streams of one row and the same four of the next (sub-stream pitch = odd number of units), so
         // lane bit 2 selects the row (group bit LOG_NS - 1) and the other lane bits fill the remaining group bits in order.
         constexpr int HB = S::LOG_NS - 1;   // log2(groups per row)
         const int low = lane & 3, rsel = (lane >> 2) & 1, rest = lane >> 3;   // 2 + 1 + 2 bits
         const int gl = low | ((rest & ((1 << (HB - 2)) - 1)) << 2) | (rsel << HB) | ((rest >> (HB - 2)) << (HB + 1));
-        constexpr int UB = S::UNP_BATCH;    // groups a lane has in flight: all loads first, then the integer work, then the stores
+        constexpr int UB = S::UNP_BATCH * NTEAM;    // groups a lane has in flight: all loads first, then the integer work, then the stores
         // a lane's groups are GSTEP apart, so both its raw address (20 bytes per group) and its destination (2 * GSTEP units on =
         // the same sub-stream, 2 * GSTEP / NS rows down) advance by compile-time constants
-        constexpr int GSTEP = 32 * NU, LD_STEP = 20 * GSTEP, ST_STEP = 2 * GSTEP / NS * 16;
+        constexpr int GSTEP = 32 * NUT, LD_STEP = 20 * GSTEP, ST_STEP = 2 * GSTEP / NS * 16;
         static_assert((2 * GSTEP) % NS == 0, "a lane must stay on one sub-stream pair");
         const int gfirst = u * 32 + gl;
         const uint32_t ld_off = 20u * (uint32_t)gfirst;
         const uint32_t st_off = (uint32_t)((2 * gfirst) & (NS - 1)) * (uint32_t)tc.a_pitch + (uint32_t)((2 * gfirst) >> S::LOG_NS) * 16u;
-        // One batch covers a lane's share of a tile (the launcher guarantees n_groups <= UB * GSTEP).  The raw words of tile
-        // k + 1 are loaded BEFORE the fence / arrive of tile k, so the shared-memory latency of the loads overlaps the drain of
-        // the stores and the integer work of a tile starts from registers; it also lets the twelve warps drift apart instead
-        // of running their load, ALU and store phases in lockstep.
+        // One batch covers a lane's share of a tile (the launcher guarantees n_groups <= UB * GSTEP).  The raw words of the
+        // team's next tile are loaded BEFORE the fence / arrive of this one, so the shared-memory latency of the loads overlaps
+        // the drain of the stores and the integer work of a tile starts from registers.
         const bool on = (p.debug_mode & 255) != 2;   // debug_mode 2: no unpack (tuning ceiling)
         bool valid[UB];
 #pragma unroll
@@ -512,13 +520,19 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
                 for (int i = 0; i < 5; ++i) rw[b][i] = valid[b] ? src[i] : 0u;
             }
         };
-        int rs = 0, as = 0;
-        uint32_t rpar = 0, epar = 1;
-        if (n_k > 0) {
-            mbar_wait_uni(&raw_full[0], 0);
-            load_raw(0);
+        // tile k lives in sample stage k % n_a (free once the MMAs of tile k - n_a are done) and raw slot k % n_raw; the cursors
+        // step by NTEAM without divisions (n_a >= 2, n_raw >= 2 > NTEAM - 1: at most one wrap per step)
+        int as = team, rs = team, rn = team;              // stage / raw slot of my tile, raw slot of my next tile
+        uint32_t epar = 1, rpar = 0;                      // parities: stage free (first pass: free), next raw slot full
+        auto step = [&](int& idx, uint32_t& par, int n) {
+            idx += NTEAM;
+            if (idx >= n) { idx -= n; par ^= 1u; }
+        };
+        if (team < n_k) {
+            mbar_wait_uni(&raw_full[rs], 0);
+            load_raw(rs);
         }
-        for (int k = 0; k < n_k; ++k) {
+        for (int k = team; k < n_k; k += NTEAM) {
             const long long t0 = p.dbg ? clock64() : 0;
             mbar_wait_uni(&a_empty[as], epar);
             const long long t2 = p.dbg ? clock64() : 0;
@@ -538,26 +552,27 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&raw_empty[rs]);   // every lane's raw words have been consumed
-            if (++rs == tc.n_raw) { rs = 0; rpar ^= 1u; }
             if (p.dbg) tw1 += clock64() - t2;
-            // next tile's raw words: now if they have landed (the usual case: the producer runs slots ahead), else after the
-            // hand-over of this stage, so that a late copy never delays the MMA of the tile just unpacked
-            const bool more = k + 1 < n_k;
-            const bool early = more && mbar_test_uni(&raw_full[rs], rpar);
-            if (early) load_raw(rs);
+            // the team's next tile: its raw words now if they have landed (the usual case: the producer runs slots ahead), else
+            // after the hand-over of this stage, so that a late copy never delays the MMA of the tile just unpacked
+            const bool more = k + NTEAM < n_k;
+            step(rn, rpar, tc.n_raw);
+            const bool early = more && mbar_test_uni(&raw_full[rn], rpar);
+            if (early) load_raw(rn);
             fence_proxy_async();   // my stores before the tensor core's reads of this stage
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[as]);
             if (u == 0) TC_TRACE(2, k);
-            if (u == NU - 1) TC_TRACE(3, k);
+            if (u == NUT - 1) TC_TRACE(3, k);
             if (u == 0 && early) TC_TRACE(9, k);
             if (more && !early) {
                 const long long t3 = p.dbg ? clock64() : 0;
-                mbar_wait_uni(&raw_full[rs], rpar);
+                mbar_wait_uni(&raw_full[rn], rpar);
                 if (p.dbg) tw0 += clock64() - t3;
-                load_raw(rs);
+                load_raw(rn);
             }
-            if (++as == tc.n_a) { as = 0; epar ^= 1u; }
+            step(as, epar, tc.n_a);
+            rs = rn;
         }
     }
 
