@@ -47,6 +47,9 @@
 #ifndef DDCB200_TC_TEAMS
 #define DDCB200_TC_TEAMS 2   // teams of unpack warps that take alternate tiles: six warps per tile, two tile times each (1: all twelve on every tile)
 #endif
+#ifndef DDCB200_TC_UBT
+#define DDCB200_TC_UBT (DDCB200_TC_UB * DDCB200_TC_TEAMS)   // batches of 16-sample groups a lane unpacks per tile of its team
+#endif
 
 // Per-tile event trace of CTA 0 (build with -DDDCB200_TC_TRACE, option dbg_counters = 3 prints it): clock64 of ten events
 // of the first 96 tiles, at p.dbg[64 + 96 * event + tile] -- how the hand-shakes of the five warp roles line up in time
@@ -86,6 +89,7 @@ struct TcShape {
     static constexpr int TILE_PACKED = TILE_S / 4 * 5;    // packed bytes per tile
     static constexpr int NUNP = DDCB200_TC_NUNP;          // unpack warps
     static constexpr int UNP_BATCH = DDCB200_TC_UB;       // 16-sample groups a lane unpacks per batch
+    static constexpr int UNP_CAP = DDCB200_TC_UBT * 32 * (DDCB200_TC_NUNP / DDCB200_TC_TEAMS);   // groups per tile the unpack warps cover
     static constexpr int NTHREADS = (8 + NUNP) * 32;
     static constexpr int HDR = 1024;
     static constexpr int LOG_NS = NS == 8 ? 3 : (NS == 16 ? 4 : 5);
@@ -495,7 +499,7 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
         constexpr int HB = S::LOG_NS - 1;   // log2(groups per row)
         const int low = lane & 3, rsel = (lane >> 2) & 1, rest = lane >> 3;   // 2 + 1 + 2 bits
         const int gl = low | ((rest & ((1 << (HB - 2)) - 1)) << 2) | (rsel << HB) | ((rest >> (HB - 2)) << (HB + 1));
-        constexpr int UB = S::UNP_BATCH * NTEAM;    // groups a lane has in flight: all loads first, then the integer work, then the stores
+        constexpr int UB = DDCB200_TC_UBT;          // groups a lane has in flight: all loads first, then the integer work, then the stores
         // a lane's groups are GSTEP apart, so both its raw address (20 bytes per group) and its destination (2 * GSTEP units on =
         // the same sub-stream, 2 * GSTEP / NS rows down) advance by compile-time constants
         constexpr int GSTEP = 32 * NUT, LD_STEP = 20 * GSTEP, ST_STEP = 2 * GSTEP / NS * 16;

@@ -43,7 +43,7 @@ TcGeom tc_geometry(int T, int D, int NS, int force_na = 0, int force_nraw = 0) {
     g.b_bytes = g.N * g.K * 2;
     g.ok = false;
     if (g.R < 1 || g.N > 256) return g;
-    if (g.n_groups > TcShape<8>::UNP_BATCH * 32 * TcShape<8>::NUNP) return g;   // one unpack batch per lane and tile
+    if (g.n_groups > TcShape<8>::UNP_CAP) return g;   // what the unpack warps of a team cover per tile
     const size_t cap = 227 * 1024;
     const size_t fixed = 1024 + (size_t)((g.b_bytes + 127) & ~127);
     // two A stages are enough for the MMA of one tile to overlap the unpack of the next (three when memory allows); everything
