@@ -25,7 +25,7 @@
 //
 // Pipeline per CTA (one per SM, persistent, 8 + NUNP warps):
 //      warp 0      TMA producer: one bulk copy of packed bytes per tile -> raw ring (up to 8 slots: HBM latency)
-//      warps 8..   unpack, in two teams that take alternate tiles: 20 bytes -> 16 fp16 per lane and group, bit-exact (PRMT,
+//      warps 8..   unpack, in NTEAM teams that take the tiles in turn: 20 bytes -> 16 fp16 per lane and group, bit-exact (PRMT,
 //                  LOP3, IMAD.WIDE, LEA.HI, HFMA2 per sample pair), raw words of the team's NEXT tile already in registers,
 //                  two STS.128 per group into the sub-streams
 //      warp 1      one elected thread issues K / 16 tcgen05.mma per tile into one of two TMEM accumulators
@@ -44,12 +44,9 @@
 #ifndef DDCB200_TC_UB
 #define DDCB200_TC_UB 3
 #endif
-#ifndef DDCB200_TC_TEAMS
-#define DDCB200_TC_TEAMS 2   // teams of unpack warps that take alternate tiles: six warps per tile, two tile times each (1: all twelve on every tile)
-#endif
-#ifndef DDCB200_TC_UBT
-#define DDCB200_TC_UBT (DDCB200_TC_UB * DDCB200_TC_TEAMS)   // batches of 16-sample groups a lane unpacks per tile of its team
-#endif
+// The unpack warps work in NTEAM teams that take the tiles in turn (template parameter of the kernel): three teams of four
+// warps where the pipeline has three or more sample stages, two teams of six where it has two -- a team must never wait for
+// a stage two phases ahead of the barrier (parity waits alias), so NTEAM <= stages.
 
 // Per-tile event trace of CTA 0 (build with -DDDCB200_TC_TRACE, option dbg_counters = 3 prints it): clock64 of ten events
 // of the first 96 tiles, at p.dbg[64 + 96 * event + tile] -- how the hand-shakes of the five warp roles line up in time
@@ -89,7 +86,7 @@ struct TcShape {
     static constexpr int TILE_PACKED = TILE_S / 4 * 5;    // packed bytes per tile
     static constexpr int NUNP = DDCB200_TC_NUNP;          // unpack warps
     static constexpr int UNP_BATCH = DDCB200_TC_UB;       // 16-sample groups a lane unpacks per batch
-    static constexpr int UNP_CAP = DDCB200_TC_UBT * 32 * (DDCB200_TC_NUNP / DDCB200_TC_TEAMS);   // groups per tile the unpack warps cover
+    static constexpr int UNP_CAP = DDCB200_TC_UB * 32 * DDCB200_TC_NUNP;   // groups per tile the unpack warps cover, with any number of teams
     static constexpr int NTHREADS = (8 + NUNP) * 32;
     static constexpr int HDR = 1024;
     static constexpr int LOG_NS = NS == 8 ? 3 : (NS == 16 ? 4 : 5);
@@ -193,7 +190,7 @@ __device__ __forceinline__ void tc_unpack16(const uint32_t (&rw)[5], uint32_t (&
     }
 }
 
-template <int D, int NS>
+template <int D, int NS, int NTEAM>
 __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(const __grid_constant__ RunParams p,
                                                                             const __grid_constant__ TcParams tc) {
     using S = TcShape<NS>;
@@ -225,8 +222,8 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
 #pragma unroll 1
         for (int s = 0; s < 8; ++s) {
             mbar_init(&raw_full[s], 1);
-            mbar_init(&raw_empty[s], NU / DDCB200_TC_TEAMS);
-            mbar_init(&a_full[s], NU / DDCB200_TC_TEAMS);
+            mbar_init(&raw_empty[s], NU / NTEAM);
+            mbar_init(&a_full[s], NU / NTEAM);
             mbar_init(&a_empty[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
@@ -489,8 +486,9 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
         // ------------------------------------------------------------------ unpack warps: NTEAM teams, team t takes the tiles
         // k = t (mod NTEAM).  With all twelve warps on every tile the stage is handed over when the slowest of them has drained its
         // stores behind the tensor core's operand reads, and the tensor pipe idled a third of every tile waiting for that
-        // (profiles/r2_tensor_engine_trace.md); a team of six has two tile times per tile (0.419 -> 0.405 ms on configs[2])
-        constexpr int NTEAM = DDCB200_TC_TEAMS, NUT = NU / NTEAM;   // teams, warps per team
+        // (profiles/r2_tensor_engine_trace.md); a team has NTEAM tile times per tile (configs[2]: 0.419 -> 0.405 -> 0.387 ms with one,
+        // two, three teams)
+        constexpr int NUT = NU / NTEAM;   // warps per team
         static_assert(NU % NTEAM == 0, "teams of equal size");
         const int team = (warp - 8) % NTEAM, u = (warp - 8) / NTEAM;   // my team takes the tiles k = team (mod NTEAM)
         // lane -> 16-sample group inside a run of 32 groups.  A quarter warp's two STS.128 must hit eight distinct 16-byte bank
@@ -499,7 +497,7 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
         constexpr int HB = S::LOG_NS - 1;   // log2(groups per row)
         const int low = lane & 3, rsel = (lane >> 2) & 1, rest = lane >> 3;   // 2 + 1 + 2 bits
         const int gl = low | ((rest & ((1 << (HB - 2)) - 1)) << 2) | (rsel << HB) | ((rest >> (HB - 2)) << (HB + 1));
-        constexpr int UB = DDCB200_TC_UBT;          // groups a lane has in flight: all loads first, then the integer work, then the stores
+        constexpr int UB = S::UNP_BATCH * NTEAM;    // groups a lane has in flight: all loads first, then the integer work, then the stores
         // a lane's groups are GSTEP apart, so both its raw address (20 bytes per group) and its destination (2 * GSTEP units on =
         // the same sub-stream, 2 * GSTEP / NS rows down) advance by compile-time constants
         constexpr int GSTEP = 32 * NUT, LD_STEP = 20 * GSTEP, ST_STEP = 2 * GSTEP / NS * 16;
@@ -525,12 +523,12 @@ __global__ void __launch_bounds__(TcShape<NS>::NTHREADS, 1) ddc_tc10_kernel(cons
             }
         };
         // tile k lives in sample stage k % n_a (free once the MMAs of tile k - n_a are done) and raw slot k % n_raw; the cursors
-        // step by NTEAM without divisions (n_a >= 2, n_raw >= 2 > NTEAM - 1: at most one wrap per step)
+        // step by NTEAM without divisions (the launcher guarantees n_a >= NTEAM; the raw ring may be shorter)
         int as = team, rs = team, rn = team;              // stage / raw slot of my tile, raw slot of my next tile
         uint32_t epar = 1, rpar = 0;                      // parities: stage free (first pass: free), next raw slot full
         auto step = [&](int& idx, uint32_t& par, int n) {
             idx += NTEAM;
-            if (idx >= n) { idx -= n; par ^= 1u; }
+            while (idx >= n) { idx -= n; par ^= 1u; }
         };
         if (team < n_k) {
             mbar_wait_uni(&raw_full[rs], 0);

@@ -69,10 +69,9 @@ struct WSCfg {
     // 10 cannot: ncu shows the FMA pipe 65 % active and DRAM at 48 % with one CTA); the ring is cut to what two CTAs can hold
     static constexpr int CTAS = (D == 4 || (D == 8 && JT > 8)) ? 2 : 1;
     static constexpr int NSLOT_FIT = NSLOT_MAX / CTAS > 16 ? 16 : NSLOT_MAX / CTAS;
-    // (the FP32-bound per-block layouts keep twelve: 0.883 against 0.903 ms with fourteen at T = 1024, D = 4; the HBM-bound whole-row
-    // tiles take all sixteen the header holds -- bytes in flight are what they lack: T = 64, D = 4 0.0808 -> 0.0790 ms; twenty
-    // slots with a wider header: 0.0807 ms again)
-    static constexpr int NSLOT = (CTAS == 2 && !WHOLE && NSLOT_FIT > 12) ? 12 : NSLOT_FIT;   // 11 at D >= 32
+    // (sixteen slots for the HBM-bound whole-row tiles measured 2 % faster at T = 64, D = 4 -- 0.0808 -> 0.0790 ms -- but one run of the
+    // GPU suite then failed in that very cell (ring_wraparound[4-64]) and could not be reproduced: twelve stays, the value every run of both rounds has used)
+    static constexpr int NSLOT = (CTAS == 2 && NSLOT_FIT > 12) ? 12 : NSLOT_FIT;   // 11 at D >= 32
     // nine slots (D = 8 beyond 64 tap blocks, two CTAs per SM): the second producer's four warps then have no slot of read-ahead;
     // a chunk takes ~30 us of FIR there, so the ~2 us refill is hidden by the other fifteen compute warps of the SM
     static_assert(NSLOT >= NGROUPS + 1 && NSLOT <= 16, "ring size");

@@ -119,9 +119,9 @@ void build_b(const ddcb200* h, double step, const TcGeom& g, __half* out, float*
         }
 }
 
-template <int D, int NS>
-int launch_tc10_t(ddcb200* h, RunParams& p, const TcParams& tc, size_t smem, cudaStream_t st) {
-    auto kern = ddc_tc10_kernel<D, NS>;
+template <int D, int NS, int NTEAM>
+int launch_tc10_n(ddcb200* h, RunParams& p, const TcParams& tc, size_t smem, cudaStream_t st) {
+    auto kern = ddc_tc10_kernel<D, NS, NTEAM>;
     static bool attr_set[64] = {};
     if (h->device < 64 && !attr_set[h->device]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -131,6 +131,13 @@ int launch_tc10_t(ddcb200* h, RunParams& p, const TcParams& tc, size_t smem, cud
     kern<<<(unsigned)grid, TcShape<NS>::NTHREADS, smem, st>>>(p, tc);
     CUDA_TRY(cudaGetLastError());
     return DDCB200_OK;
+}
+
+// three teams of unpack warps where there are three sample stages for them, two otherwise (ddc_kernel_tc.cuh)
+template <int D, int NS>
+int launch_tc10_t(ddcb200* h, RunParams& p, const TcParams& tc, size_t smem, cudaStream_t st) {
+    // (a team per stage AND per raw slot at most: a parity wait two phases ahead of its barrier would alias)
+    return (tc.n_a >= 3 && tc.n_raw >= 3) ? launch_tc10_n<D, NS, 3>(h, p, tc, smem, st) : launch_tc10_n<D, NS, 2>(h, p, tc, smem, st);
 }
 
 }  // namespace
