@@ -604,125 +604,138 @@ def run_extras(args, torch, dev, local, gen_input, time_device, parity_window, h
     extra = {}
 
     # ---- configs[2]: 64 streams x 2^24 packed 10-bit samples ---------------------------------------------------------
-    s3, n3 = 64, 1 << 24
-    ddc = DigitalDownConverter(D, FS, csv107, device=local)
-    m3 = ddc.out_len(n3)
-    x3 = gen_input(s3, n3, True, seed=777)
-    y3 = torch.empty((s3, m3), dtype=torch.complex64, device=dev)
-    steps3 = 10
-    ms3 = time_device(ddc, x3, y3, True, steps3, 3) / steps3
-    v3 = ddc.last_variant
-    err3 = parity_window(ddc, x3, y3, True, n3, T, D, seed=3)
-    ddc.set_option("packed_engine", 0)          # the same workload on the CUDA-core fused-unpack kernel, for comparison
-    ms3c = time_device(ddc, x3, y3, True, steps3, 3) / steps3
-    v3c = ddc.last_variant
-    err3c = parity_window(ddc, x3, y3, True, n3, T, D, seed=3)
-    ddc.set_option("packed_engine", 1)
-    h_in = torch.empty(x3.shape, dtype=torch.uint8, pin_memory=True)
-    h_in.copy_(x3)
-    h_out = torch.empty((s3, m3), dtype=torch.complex64, pin_memory=True)
-    torch.cuda.synchronize()
-    step3 = ddc.phase_step(n3, FC)
-    hnd = ddc._get_handle()
-    e2e_t = []
-    for i in range(3):
-        t0 = time.perf_counter()
-        _lib.check(lib.ddcb200_run_host_packed10(hnd, h_in.data_ptr(), n3, s3, h_in.stride(0), step3, 0, h_out.data_ptr(), m3))
-        e2e_t.append(time.perf_counter() - t0)
-    e2e3 = min(e2e_t[1:])
-    extra["c3"] = {
-        "workload": "64 streams x 2^24 packed 10-bit samples, 256 taps, decimation 16 (BASELINE configs[2])",
-        "ms": ms3, "gsamples_per_s": s3 * n3 / ms3 / 1e6, "steps": steps3, "kernel": v3, "parity_max_err": err3,
-        "roofline": roofline_of(s3, n3, m3, T, D, True, ms3 * 1e-3, v3, hbm_peak, peak_src, ncu_traffic("c3", v3)),
-        "e2e": {"value": s3 * n3 / e2e3 / 1e9, "unit": "Gsamples/s", "ms_per_step": e2e3 * 1e3,
-                "h2d_bytes_per_step": x3.numel(), "d2h_bytes_per_step": s3 * m3 * 8},
-        "cuda_cores": {"ms": ms3c, "gsamples_per_s": s3 * n3 / ms3c / 1e6, "kernel": v3c, "parity_max_err": err3c,
-                       "hbm_frac": roofline_of(s3, n3, m3, T, D, True, ms3c * 1e-3, v3c, hbm_peak, peak_src)["frac"],
-                       "note": "option packed_engine = 0: the round-1 fused-unpack kernel"},
-    }
-    del x3, y3, h_in, h_out
-    ddc.close()
-    torch.cuda.empty_cache()
+    def _c3():
+        s3, n3 = 64, 1 << 24
+        ddc = DigitalDownConverter(D, FS, csv107, device=local)
+        m3 = ddc.out_len(n3)
+        x3 = gen_input(s3, n3, True, seed=777)
+        y3 = torch.empty((s3, m3), dtype=torch.complex64, device=dev)
+        steps3 = 10
+        ms3 = time_device(ddc, x3, y3, True, steps3, 3) / steps3
+        v3 = ddc.last_variant
+        err3 = parity_window(ddc, x3, y3, True, n3, T, D, seed=3)
+        ddc.set_option("packed_engine", 0)          # the same workload on the CUDA-core fused-unpack kernel, for comparison
+        ms3c = time_device(ddc, x3, y3, True, steps3, 3) / steps3
+        v3c = ddc.last_variant
+        err3c = parity_window(ddc, x3, y3, True, n3, T, D, seed=3)
+        ddc.set_option("packed_engine", 1)
+        h_in = torch.empty(x3.shape, dtype=torch.uint8, pin_memory=True)
+        h_in.copy_(x3)
+        h_out = torch.empty((s3, m3), dtype=torch.complex64, pin_memory=True)
+        torch.cuda.synchronize()
+        step3 = ddc.phase_step(n3, FC)
+        hnd = ddc._get_handle()
+        e2e_t = []
+        for i in range(3):
+            t0 = time.perf_counter()
+            _lib.check(lib.ddcb200_run_host_packed10(hnd, h_in.data_ptr(), n3, s3, h_in.stride(0), step3, 0, h_out.data_ptr(), m3))
+            e2e_t.append(time.perf_counter() - t0)
+        e2e3 = min(e2e_t[1:])
+        extra["c3"] = {
+            "workload": "64 streams x 2^24 packed 10-bit samples, 256 taps, decimation 16 (BASELINE configs[2])",
+            "ms": ms3, "gsamples_per_s": s3 * n3 / ms3 / 1e6, "steps": steps3, "kernel": v3, "parity_max_err": err3,
+            "roofline": roofline_of(s3, n3, m3, T, D, True, ms3 * 1e-3, v3, hbm_peak, peak_src, ncu_traffic("c3", v3)),
+            "e2e": {"value": s3 * n3 / e2e3 / 1e9, "unit": "Gsamples/s", "ms_per_step": e2e3 * 1e3,
+                    "h2d_bytes_per_step": x3.numel(), "d2h_bytes_per_step": s3 * m3 * 8},
+            "cuda_cores": {"ms": ms3c, "gsamples_per_s": s3 * n3 / ms3c / 1e6, "kernel": v3c, "parity_max_err": err3c,
+                           "hbm_frac": roofline_of(s3, n3, m3, T, D, True, ms3c * 1e-3, v3c, hbm_peak, peak_src)["frac"],
+                           "note": "option packed_engine = 0: the round-1 fused-unpack kernel"},
+        }
+        del x3, y3, h_in, h_out
+        ddc.close()
+        torch.cuda.empty_cache()
 
     # ---- configs[3]: taps 64 .. 1024 x decimation 4 .. 64, N = 2^26 float32 (256 MiB per launch > L2) ------------------
-    n4 = 1 << 26
-    x4 = gen_input(1, n4, False, seed=4242)
-    x4p = None
-    sweep, sweep_packed = [], []
-    for t in (64, 128, 256, 512, 1024):
-        for d in (4, 8, 16, 32, 64):
-            if t == 256:
-                csv = csv107
-            else:
-                csv = os.path.join(tmp, f"firwin_{t}_{d}.csv")
-                np.savetxt(csv, signal.firwin(t, 0.8 / d), fmt="%.18e")
-            c = DigitalDownConverter(d, FS, csv, device=local)
-            m4 = c.out_len(n4)
-            y4 = torch.empty((1, m4), dtype=torch.complex64, device=dev)
-            for pk, dst in ((False, sweep), (True, sweep_packed)):
-                if pk and x4p is None:
-                    from dc_sand_b200 import cwg as dcwg
+    def _sweep():
+        n4 = 1 << 26
+        x4 = gen_input(1, n4, False, seed=4242)
+        x4p = None
+        sweep, sweep_packed = [], []
+        for t in (64, 128, 256, 512, 1024):
+            for d in (4, 8, 16, 32, 64):
+                if t == 256:
+                    csv = csv107
+                else:
+                    csv = os.path.join(tmp, f"firwin_{t}_{d}.csv")
+                    np.savetxt(csv, signal.firwin(t, 0.8 / d), fmt="%.18e")
+                c = DigitalDownConverter(d, FS, csv, device=local)
+                m4 = c.out_len(n4)
+                y4 = torch.empty((1, m4), dtype=torch.complex64, device=dev)
+                for pk, dst in ((False, sweep), (True, sweep_packed)):
+                    if pk and x4p is None:
+                        from dc_sand_b200 import cwg as dcwg
 
-                    x4p = dcwg.pack10_gpu(x4)
-                xin = x4p if pk else x4
-                ms = time_device(c, xin, y4, pk, 10, 3) / 10
-                var = c.last_variant
-                r = roofline_of(1, n4, m4, t, d, pk, ms * 1e-3, var, hbm_peak, peak_src)
-                dst.append({"taps": t, "decimation": d, "ms": ms, "gsamples_per_s": n4 / ms / 1e6, "kernel": var.split("<")[0],
-                            "bound": r["bound"], "hbm_frac": r["frac"], "fp32_executed_frac": r["fp32_executed_frac"],
-                            "floor_frac": r["floor_frac"],
-                            "parity_max_err": parity_window(c, xin, y4, pk, n4, t, d, seed=t + d)})
-                if pk:   # the same cell on the CUDA-core kernels (option packed_engine = 0)
-                    c.set_option("packed_engine", 0)
-                    msc = time_device(c, xin, y4, pk, 10, 3) / 10
-                    dst[-1].update({"ms_cuda_cores": msc, "kernel_cuda_cores": c.last_variant.split("<")[0]})
-                    c.set_option("packed_engine", 1)
-            del y4
-            c.close()
-    extra["sweep"] = {"workload": "1 stream x 2^26 float32 samples, firwin(T, 0.8 / D) taps (the shipped 107 MHz filter at T = 256); "
-                                  "3 warm-up + 10 launches per cell (BASELINE configs[3])", "cells": sweep}
-    extra["sweep_packed"] = {"workload": "the same cells on the packed 10-bit form of the same samples: default engine (tcgen05 tensor "
-                                         "cores, unpack fused in every cell) and, as ms_cuda_cores, the CUDA-core kernels", "cells": sweep_packed}
-    del x4p
-    torch.cuda.empty_cache()
+                        x4p = dcwg.pack10_gpu(x4)
+                    xin = x4p if pk else x4
+                    ms = time_device(c, xin, y4, pk, 10, 3) / 10
+                    var = c.last_variant
+                    r = roofline_of(1, n4, m4, t, d, pk, ms * 1e-3, var, hbm_peak, peak_src)
+                    dst.append({"taps": t, "decimation": d, "ms": ms, "gsamples_per_s": n4 / ms / 1e6, "kernel": var.split("<")[0],
+                                "bound": r["bound"], "hbm_frac": r["frac"], "fp32_executed_frac": r["fp32_executed_frac"],
+                                "floor_frac": r["floor_frac"],
+                                "parity_max_err": parity_window(c, xin, y4, pk, n4, t, d, seed=t + d)})
+                    if pk:   # the same cell on the CUDA-core kernels (option packed_engine = 0)
+                        c.set_option("packed_engine", 0)
+                        msc = time_device(c, xin, y4, pk, 10, 3) / 10
+                        dst[-1].update({"ms_cuda_cores": msc, "kernel_cuda_cores": c.last_variant.split("<")[0]})
+                        c.set_option("packed_engine", 1)
+                del y4
+                c.close()
+        extra["sweep"] = {"workload": "1 stream x 2^26 float32 samples, firwin(T, 0.8 / D) taps (the shipped 107 MHz filter at T = 256); "
+                                      "3 warm-up + 10 launches per cell (BASELINE configs[3])", "cells": sweep}
+        extra["sweep_packed"] = {"workload": "the same cells on the packed 10-bit form of the same samples: default engine (tcgen05 tensor "
+                                             "cores, unpack fused in every cell) and, as ms_cuda_cores, the CUDA-core kernels", "cells": sweep_packed}
+        del x4, x4p
+        torch.cuda.empty_cache()
 
     # ---- DigitalDownConverter.run(): the reference's own call, pageable float32 NumPy in, complex128 out (2^26 samples) ----
-    x_np = x4[0].cpu().numpy()
-    del x4
-    ddc = DigitalDownConverter(D, FS, csv107, device=local)
-    ddc.run(x_np[: 1 << 22], FC)
-    tr = []
-    for i in range(3):
-        t0 = time.perf_counter()
-        y = ddc.run(x_np, FC)
-        tr.append(time.perf_counter() - t0)
-    best = min(tr)
-    extra["e2e_run_api"] = {
-        "api": "DigitalDownConverter.run(np.ndarray float32 [2^26] pageable, 100e6) -> complex128 (feng/ddc/src/ddc.py:121)",
-        "value": n4 / best / 1e9, "unit": "Gsamples/s", "ms_per_call": best * 1e3, "calls": 3,
-        "h2d_bytes_per_step": x_np.nbytes, "d2h_bytes_per_step": int(y.shape[0]) * 8, "out_dtype": str(y.dtype),
-    }
-    del x_np, y
-    ddc.close()
+    def _run_api():
+        n4 = 1 << 26
+        x_np = gen_input(1, n4, False, seed=4242)[0].cpu().numpy()   # the sweep's samples
+        ddc = DigitalDownConverter(D, FS, csv107, device=local)
+        ddc.run(x_np[: 1 << 22], FC)
+        tr = []
+        for i in range(3):
+            t0 = time.perf_counter()
+            y = ddc.run(x_np, FC)
+            tr.append(time.perf_counter() - t0)
+        best = min(tr)
+        extra["e2e_run_api"] = {
+            "api": "DigitalDownConverter.run(np.ndarray float32 [2^26] pageable, 100e6) -> complex128 (feng/ddc/src/ddc.py:121)",
+            "value": n4 / best / 1e9, "unit": "Gsamples/s", "ms_per_call": best * 1e3, "calls": 3,
+            "h2d_bytes_per_step": x_np.nbytes, "d2h_bytes_per_step": int(y.shape[0]) * 8, "out_dtype": str(y.dtype),
+        }
+        del x_np, y
+        ddc.close()
 
     # ---- configs[4] at G = 1: the 128-stream workload on ONE GPU (8 GiB in, 1 GiB out) -------------------------------------
-    s5, n5 = TOTAL_STREAMS_C5, 1 << 24
-    ddc = DigitalDownConverter(D, FS, csv107, device=local)
-    m5 = ddc.out_len(n5)
-    x5 = gen_input(s5, n5, False, seed=1234)
-    y5 = torch.empty((s5, m5), dtype=torch.complex64, device=dev)
-    steps5 = 5
-    ms5 = time_device(ddc, x5, y5, False, steps5, 3) / steps5
-    v5 = ddc.last_variant
-    extra["c5_g1"] = {
-        "workload": "128 streams x 2^24 float32 samples on ONE GPU (BASELINE configs[4] at G = 1: strong-scaling denominator)",
-        "ms": ms5, "gsamples_per_s": s5 * n5 / ms5 / 1e6, "steps": steps5, "kernel": v5,
-        "parity_max_err": parity_window(ddc, x5, y5, False, n5, T, D, seed=5),
-        "roofline": roofline_of(s5, n5, m5, T, D, False, ms5 * 1e-3, v5, hbm_peak, peak_src),
-    }
-    del x5, y5
-    ddc.close()
-    torch.cuda.empty_cache()
+    def _c5_g1():
+        s5, n5 = TOTAL_STREAMS_C5, 1 << 24
+        ddc = DigitalDownConverter(D, FS, csv107, device=local)
+        m5 = ddc.out_len(n5)
+        x5 = gen_input(s5, n5, False, seed=1234)
+        y5 = torch.empty((s5, m5), dtype=torch.complex64, device=dev)
+        steps5 = 5
+        ms5 = time_device(ddc, x5, y5, False, steps5, 3) / steps5
+        v5 = ddc.last_variant
+        extra["c5_g1"] = {
+            "workload": "128 streams x 2^24 float32 samples on ONE GPU (BASELINE configs[4] at G = 1: strong-scaling denominator)",
+            "ms": ms5, "gsamples_per_s": s5 * n5 / ms5 / 1e6, "steps": steps5, "kernel": v5,
+            "parity_max_err": parity_window(ddc, x5, y5, False, n5, T, D, seed=5),
+            "roofline": roofline_of(s5, n5, m5, T, D, False, ms5 * 1e-3, v5, hbm_peak, peak_src),
+        }
+        del x5, y5
+        ddc.close()
+        torch.cuda.empty_cache()
+    # every section on its own: a failure in one of them (say, no room for the 9 GiB of configs[4] on a shared device) must not
+    # cost the headline line or the other sections; it is reported in place of the section's numbers
+    for keys, section in ((("c3",), _c3), (("sweep", "sweep_packed"), _sweep), (("e2e_run_api",), _run_api), (("c5_g1",), _c5_g1)):
+        try:
+            section()
+        except Exception as e:   # noqa: BLE001 -- reported, not swallowed
+            for k in keys:
+                extra.setdefault(k, {"error": f"{type(e).__name__}: {e}"})
+            torch.cuda.empty_cache()
     return extra
 
 
