@@ -17,6 +17,7 @@ SIGNATURES = {
     "ddcb200_set_decimation": (C.c_int, [C.c_void_p, C.c_int]),
     "ddcb200_out_len": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
     "ddcb200_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]),
+    "ddcb200_tensor_engine_geometry": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int32)]),
     "ddcb200_run_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int64,
                                   C.c_void_p, C.c_int64, C.c_void_p]),
     "ddcb200_run_packed10": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int64,

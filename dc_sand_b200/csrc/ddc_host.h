@@ -103,6 +103,7 @@ int launch_w(ddcb200* h, RunParams& p, cudaStream_t st, double step, int D, int 
 int launch_w10s(ddcb200* h, RunParams& p, cudaStream_t st, double step);                                              // k_w10.cu
 bool tc10_supported(const ddcb200* h, int n_taps, int D);                                                                               // k_tc.cu
 int launch_tc10(ddcb200* h, RunParams& p, cudaStream_t st, double step, int D);                                       // k_tc.cu
+int tc10_describe(int n_taps, int D, int32_t out[12]);                                                                // k_tc.cu
 int launch_ws(ddcb200* h, RunParams& p, const float* d_in, long long n_rows, cudaStream_t st, double step, int D, int jt);   // k_ws*.cu
 int launch_ws4(ddcb200* h, RunParams& p, const float* d_in, long long n_rows, cudaStream_t st, double step, int jt);
 int launch_ws8(ddcb200* h, RunParams& p, const float* d_in, long long n_rows, cudaStream_t st, double step, int jt);

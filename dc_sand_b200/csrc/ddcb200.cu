@@ -219,6 +219,7 @@ unsigned long long phase_of(double step, int64_t sample_offset) {
 int ensure_ring(ddcb200* h, int n_taps) {
     if (n_taps <= h->ring_cap) return DDCB200_OK;
     const int cap = std::max(n_taps, 1024);
+    h->ring_cap = 0;   // only valid again once every slot has been allocated (a failure below leaves null slots behind)
     for (int i = 0; i < ddcb200::kRing; ++i) {
         if (h->d_ctaps[i]) cudaFree(h->d_ctaps[i]);
         if (h->h_ctaps[i]) cudaFreeHost(h->h_ctaps[i]);
@@ -696,6 +697,11 @@ int ddcb200_plan(int n_taps, int decimation, int packed, int aligned, int varian
         snprintf(name, (size_t)name_cap, "%s", kFamilyName[pl.family]);
     }
     return pl.jt;
+}
+
+int ddcb200_tensor_engine_geometry(int n_taps, int decimation, int32_t* out12) {
+    if (!out12) return fail(DDCB200_EINVAL, "tensor_engine_geometry: null output");
+    return ddch::tc10_describe(n_taps, decimation, out12);
 }
 
 int ddcb200_set_taps(ddcb200_t* h, const double* taps, int n_taps) {
@@ -1184,6 +1190,8 @@ int session_push_dev(ddcb200_session_t* s, const void* d_in, bool packed, int64_
     if (m > 0 && (!d_out || out_stride < m)) return fail(DDCB200_EINVAL, "session_push: output too small for %lld outputs", (long long)m);
     DeviceGuard g(s->h->device);
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : s->h->stream;
+    // the previous device push may have come on another stream: its kernel and tail copy still own the work buffers
+    if (s->user_pending) CUDA_TRY(cudaStreamWaitEvent(st, s->ev_user, 0));
     CUDA_TRY(copy_rows_async(s->work[s->cur] + s->bytes(s->carry), (size_t)s->pitch, d_in, (size_t)in_stride * (packed ? 1 : 4),
                              s->bytes(n_samples), (size_t)s->n_streams, cudaMemcpyDeviceToDevice, st));
     int rc = stream_step(s, n_samples, d_out, out_stride, n_out, st);

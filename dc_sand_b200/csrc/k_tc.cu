@@ -160,6 +160,18 @@ bool tc10_supported(const ddcb200* h, int T, int D) {
     return tc_pick(h, T, D).ok;
 }
 
+// the pipeline the engine would run for (n_taps, D) with default options: see ddcb200_tensor_engine_geometry (include/ddcb200.h)
+int tc10_describe(int T, int D, int32_t out[12]) {
+    if (!(D == 4 || D == 8 || D == 16 || D == 32 || D == 64) || T < 1) return 0;
+    const TcGeom g = tc_pick(nullptr, T, D);
+    if (!g.ok) return 0;
+    const int teams = (g.n_a >= 3 && g.n_raw >= 3) ? 3 : 2;   // launch_tc10_t
+    const int32_t v[12] = {g.row_s, g.N, g.K, g.n_a, g.n_raw, teams, (int32_t)g.smem, g.n_groups,
+                           TcShape<8>::UNP_CAP, g.a_pitch, g.raw_bytes, g.b_bytes};
+    std::memcpy(out, v, sizeof(v));
+    return 1;
+}
+
 int launch_tc10(ddcb200* h, RunParams& p, cudaStream_t st, double step, int D) {
     const int T = (int)h->taps.size();
     const TcGeom g = tc_pick(h, T, D);

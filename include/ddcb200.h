@@ -71,6 +71,14 @@ int64_t ddcb200_out_len(int64_t n_samples, int n_taps, int decimation);
  * it has none), or a negative DDCB200_E* code. */
 int ddcb200_plan(int n_taps, int decimation, int packed, int aligned, int variant, int packed_engine, char* name, int name_cap);
 
+/* Shared-memory pipeline of the tensor-core engine for packed input (the fused form of the stub ddc.py:68-83 followed by
+ * ddc.py:51-119) at (n_taps, decimation) with default options -- pure host arithmetic, so the engine's sizing rules can be
+ * checked without a GPU.  Returns 1 and fills out12 = {samples per MMA row, accumulator columns N, K, sample stages, raw
+ * slots, unpack teams, shared-memory bytes, 16-sample groups per tile, groups the unpack warps cover per tile, sub-stream
+ * pitch in bytes, packed bytes copied per tile, tap-matrix bytes}; returns 0 where the engine is not built or does not fit
+ * (the dispatcher then takes the CUDA-core kernels); DDCB200_EINVAL for a null pointer. */
+int ddcb200_tensor_engine_geometry(int n_taps, int decimation, int32_t* out12);
+
 /* ---- device-resident entry points (inputs and outputs already in HBM) ------------------------------------
  * Replace _mix + _bandpass_fir_filter + _decimate (ddc.py:51-66, 85-100, 102-119) and the NCO generation of
  * cwg.generate_carrier_wave(complex=True) (cwg.py:31-36) for `n_streams` independent 1-D streams.

@@ -77,6 +77,47 @@ def test_kernel_selection_table():
     assert _lib.load().ddcb200_plan(256, 16, 0, 1, 0, 1, buf, 8) == _lib.EINVAL
 
 
+def test_tensor_engine_pipeline_sizing_rules():
+    """The tensor-core engine's shared-memory pipeline (ddcb200_tensor_engine_geometry, csrc/k_tc.cu) over every filter length
+    1 .. 2100 at every decimation it is built for.  The kernel's hand-shakes rest on these rules (csrc/ddc_kernel_tc.cuh):
+    a team of unpack warps per sample stage AND per raw slot at most (a parity wait two phases ahead of its mbarrier would
+    alias), the unpack warps cover every 16-sample group of a tile, K is a whole number of MMAs and holds the row plus the
+    filter's overhang, the accumulator pair fits tensor memory, everything fits 227 KB and the 14-bit descriptor fields."""
+    lib = _lib.load()
+    out = (ctypes.c_int32 * 12)()
+    assert lib.ddcb200_tensor_engine_geometry(256, 16, None) == _lib.EINVAL
+    assert lib.ddcb200_tensor_engine_geometry(256, 12, out) == 0 and lib.ddcb200_tensor_engine_geometry(0, 16, out) == 0
+    fits = {}
+    for d in (4, 8, 16, 32, 64):
+        last = 0
+        for t in range(1, 2101):
+            if not lib.ddcb200_tensor_engine_geometry(t, d, out):
+                continue
+            row_s, n, k, n_a, n_raw, teams, smem, groups, cap, pitch, raw_bytes, b_bytes = list(out)
+            last = t
+            assert row_s in (64, 128) and row_s % d == 0
+            assert n == max(16, 4 * row_s // d) and n % 16 == 0 and 2 * n <= 512          # two accumulators in tensor memory
+            assert k % 16 == 0 and row_s - d + t <= k < row_s - d + t + 16
+            assert 2 <= n_a <= 3 and 2 <= n_raw <= 8
+            assert teams in (2, 3) and teams <= n_a and teams <= n_raw and 12 % teams == 0
+            assert groups * 16 == 128 * row_s + k - row_s and groups <= cap
+            assert raw_bytes % 16 == 0 and raw_bytes >= 20 * groups                         # bulk copies: whole 16-byte pieces
+            assert pitch % 16 == 0 and (pitch // 16) % 2 == 1                                # odd unit pitch: conflict-free stores
+            assert pitch * (row_s // 8) >= 2 * groups * 16                                   # a stage holds the tile's fp16 samples
+            assert b_bytes == n * k * 2
+            assert smem <= 227 * 1024 and smem // 16 < (1 << 14)
+            assert smem >= 1024 + b_bytes + n_a * pitch * (row_s // 8) + n_raw * raw_bytes
+        fits[d] = last
+    # the BASELINE sweep (taps 64 .. 1024 x decimation 4 .. 64) lies inside the engine at every decimation; configs[2] gets
+    # 128-sample rows, three sample stages and three teams
+    assert all(v >= 1024 for v in fits.values()), fits
+    assert lib.ddcb200_tensor_engine_geometry(256, 16, out) == 1
+    assert list(out)[:6] == [128, 32, 368, 3, 5, 3]
+    # where the geometry says no, the dispatcher goes to the CUDA cores
+    for t, d in ((fits[4] + 1, 4), (2100, 4)):
+        assert lib.ddcb200_tensor_engine_geometry(t, d, out) == 0 and _plan(t, d, packed=1)[0].startswith("unpack+f32")
+
+
 def test_host_thread_pool(tmp_path):
     """The pool of parked host threads that stages pageable input and widens complex128 output (csrc/host_pool.h): a C++
     stress test, under ThreadSanitizer when g++ links it."""
