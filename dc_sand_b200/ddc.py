@@ -319,6 +319,8 @@ class DigitalDownConverter:
         m = self.out_len(n)
         if out is None:
             out = torch.empty((s, m), dtype=torch.complex64, device=x.device)
+        if not out.is_cuda or out.device != x.device:
+            raise ValueError(f"out must live on cuda:{self.device} like x")   # a host pointer would fault inside the kernel
         out2 = out.unsqueeze(0) if out.dim() == 1 else out
         if out2.shape != (s, m) or out2.dtype != torch.complex64 or out2.stride(1) != 1:
             raise ValueError("out must be complex64 [streams, M] with contiguous rows")

@@ -104,6 +104,8 @@ class DDCStream:
         packed session), n <= max_chunk."""
         import torch
 
+        if not x.is_cuda or x.device.index != self.ddc.device:
+            raise ValueError(f"x must live on cuda:{self.ddc.device}")
         one_d = x.dim() == 1
         x2 = x.unsqueeze(0) if one_d else x
         want = torch.uint8 if self.packed else torch.float32
@@ -115,6 +117,8 @@ class DDCStream:
         m = self.out_len(n)
         if out is None:
             out = torch.empty((self.n_streams, m), dtype=torch.complex64, device=x.device)
+        if not out.is_cuda or out.device != x.device:
+            raise ValueError(f"out must live on cuda:{self.ddc.device} like x")
         out2 = out.unsqueeze(0) if out.dim() == 1 else out
         if out2.shape[0] != self.n_streams or out2.shape[1] < m or out2.dtype != torch.complex64 or out2.stride(1) != 1:
             raise ValueError("out must be complex64 [streams, >= m] with contiguous rows")
